@@ -1,0 +1,169 @@
+/*
+ * pe_host.c -- TEST INFRASTRUCTURE (oracle), not product code.
+ *
+ * Runs the reference's own dynamics library -- the Simulink-Coder DLL that
+ * core/model.py:104-126 loads (core/model_simple_win64.dll) -- natively on an
+ * x86-64 Linux host.  The DLL image is embedded into this shared object at
+ * build time (oracle/Makefile, `.incbin` of the file where it lies under
+ * /root/reference); nothing of the reference is copied into the repository.
+ *
+ * How: a PE32+ image is just code + data.  Each `b747ref_open()` maps a private
+ * copy of the sections, applies the base relocations (so any number of
+ * independent instances can live in one process -- the reference gets the
+ * same isolation by copying the DLL file per Model, core/model.py:99-110),
+ * points every import-table slot at a trap (the numeric path never calls
+ * into KERNEL32), and resolves the export directory.  DllMain / CRT start-up
+ * is deliberately NOT run, so the statically linked UCRT libm keeps its
+ * file-default ISA flags (SSE2 path).  Exports are `void f(void)` and are
+ * called through the Microsoft x64 ABI.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may use this file's output (oracle/_ref/).
+ */
+#define _GNU_SOURCE
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+
+#ifndef B747_DLL_PATH
+#error "build with -DB747_DLL_PATH=\"/root/reference/core/model_simple_win64.dll\""
+#endif
+
+__asm__(
+    ".section .rodata\n"
+    ".balign 16\n"
+    ".globl b747ref_image_begin\n"
+    "b747ref_image_begin:\n"
+    ".incbin \"" B747_DLL_PATH "\"\n"
+    ".globl b747ref_image_end\n"
+    "b747ref_image_end:\n"
+    ".previous\n");
+extern const uint8_t b747ref_image_begin[], b747ref_image_end[];
+
+typedef void(__attribute__((ms_abi)) * ms_void_fn)(void);
+
+typedef struct b747ref_inst {
+  uint8_t *img;      /* mapped image */
+  uint32_t img_size; /* SizeOfImage */
+  uint32_t exp_rva;  /* export directory RVA */
+  /* writable sections (for snapshot/restore) */
+  uint32_t n_rw;
+  uint32_t rw_rva[8], rw_size[8];
+} b747ref_inst;
+
+static void __attribute__((ms_abi)) import_trap(void) {
+  fprintf(stderr, "b747ref: the DLL called into an import (Win32/CRT path) -- not supported\n");
+  abort();
+}
+
+static inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+b747ref_inst *b747ref_open(void) {
+  const uint8_t *file = b747ref_image_begin;
+  size_t file_size = (size_t)(b747ref_image_end - b747ref_image_begin);
+  if (file_size < 0x400 || rd16(file) != 0x5a4d) return NULL;
+  uint32_t nt = rd32(file + 0x3c);
+  if (rd32(file + nt) != 0x00004550) return NULL;
+  const uint8_t *fh = file + nt + 4;      /* IMAGE_FILE_HEADER */
+  uint16_t n_sections = rd16(fh + 2);
+  uint16_t opt_size = rd16(fh + 16);
+  const uint8_t *opt = fh + 20;           /* IMAGE_OPTIONAL_HEADER64 */
+  if (rd16(opt) != 0x20b) return NULL;    /* PE32+ only */
+  uint64_t preferred = rd64(opt + 24);
+  uint32_t img_size = rd32(opt + 56);
+  uint32_t hdr_size = rd32(opt + 60);
+  const uint8_t *dirs = opt + 112;        /* data directories */
+  uint32_t exp_rva = rd32(dirs + 0 * 8);
+  uint32_t imp_rva = rd32(dirs + 1 * 8);
+  uint32_t rel_rva = rd32(dirs + 5 * 8), rel_size = rd32(dirs + 5 * 8 + 4);
+
+  uint8_t *img = mmap(NULL, img_size, PROT_READ | PROT_WRITE | PROT_EXEC,
+                      MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (img == MAP_FAILED) return NULL;
+  b747ref_inst *in = calloc(1, sizeof *in);
+  in->img = img; in->img_size = img_size; in->exp_rva = exp_rva;
+
+  memcpy(img, file, hdr_size);
+  const uint8_t *sec = opt + opt_size;
+  for (unsigned i = 0; i < n_sections; i++, sec += 40) {
+    uint32_t vsize = rd32(sec + 8), va = rd32(sec + 12), raw_size = rd32(sec + 16), raw_off = rd32(sec + 20);
+    uint32_t flags = rd32(sec + 36);
+    if (raw_size) memcpy(img + va, file + raw_off, raw_size < vsize || !vsize ? raw_size : vsize);
+    if ((flags & 0x80000000u) && in->n_rw < 8) { /* IMAGE_SCN_MEM_WRITE */
+      in->rw_rva[in->n_rw] = va;
+      in->rw_size[in->n_rw] = vsize ? vsize : raw_size;
+      in->n_rw++;
+    }
+  }
+  /* base relocations: blocks of {page_rva, block_size, uint16 entries[]}; type 10 = DIR64 */
+  int64_t delta = (int64_t)((uint64_t)img - preferred);
+  if (delta && rel_size) {
+    uint8_t *p = img + rel_rva, *end = p + rel_size;
+    while (p + 8 <= end) {
+      uint32_t page = rd32(p), bsz = rd32(p + 4);
+      if (bsz < 8) break;
+      for (uint32_t k = 8; k + 2 <= bsz; k += 2) {
+        uint16_t e = rd16(p + k);
+        if ((e >> 12) == 10) {
+          uint8_t *slot = img + page + (e & 0xfff);
+          uint64_t v = rd64(slot) + (uint64_t)delta;
+          memcpy(slot, &v, 8);
+        }
+      }
+      p += bsz;
+    }
+  }
+  /* import table: every IAT slot -> trap */
+  if (imp_rva) {
+    for (uint8_t *d = img + imp_rva; rd32(d + 12); d += 20) {
+      uint64_t *iat = (uint64_t *)(img + rd32(d + 16));
+      for (; *iat; iat++) *iat = (uint64_t)(uintptr_t)import_trap;
+    }
+  }
+  return in;
+}
+
+void b747ref_close(b747ref_inst *in) {
+  if (!in) return;
+  munmap(in->img, in->img_size);
+  free(in);
+}
+
+void *b747ref_sym(b747ref_inst *in, const char *name) {
+  const uint8_t *e = in->img + in->exp_rva;
+  uint32_t n_names = rd32(e + 24);
+  const uint32_t *funcs = (const uint32_t *)(in->img + rd32(e + 28));
+  const uint32_t *names = (const uint32_t *)(in->img + rd32(e + 32));
+  const uint16_t *ords = (const uint16_t *)(in->img + rd32(e + 36));
+  for (uint32_t i = 0; i < n_names; i++)
+    if (!strcmp((const char *)in->img + names[i], name)) return in->img + funcs[ords[i]];
+  return NULL;
+}
+
+void *b747ref_rva(b747ref_inst *in, uint32_t rva) { return in->img + rva; }
+
+void b747ref_call(void *fn) { ((ms_void_fn)fn)(); }
+
+void b747ref_call_n(void *fn, long n) {
+  ms_void_fn f = (ms_void_fn)fn;
+  for (long i = 0; i < n; i++) f();
+}
+
+/* snapshot / restore of all writable sections (lets one instance multiplex envs) */
+size_t b747ref_state_size(b747ref_inst *in) {
+  size_t s = 0;
+  for (uint32_t i = 0; i < in->n_rw; i++) s += in->rw_size[i];
+  return s;
+}
+void b747ref_state_save(b747ref_inst *in, void *buf) {
+  uint8_t *b = buf;
+  for (uint32_t i = 0; i < in->n_rw; i++) { memcpy(b, in->img + in->rw_rva[i], in->rw_size[i]); b += in->rw_size[i]; }
+}
+void b747ref_state_load(b747ref_inst *in, const void *buf) {
+  const uint8_t *b = buf;
+  for (uint32_t i = 0; i < in->n_rw; i++) { memcpy(in->img + in->rw_rva[i], b, in->rw_size[i]); b += in->rw_size[i]; }
+}
