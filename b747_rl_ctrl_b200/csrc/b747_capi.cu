@@ -1,0 +1,386 @@
+// b747_capi.cu -- the C ABI of libb747_b200.so (include/b747.h).  Host-side glue only: device
+// memory, streams, launches.  There is no CPU implementation behind any entry point.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b747_kernels.h"
+
+using namespace b747;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(B747_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+struct b747_handle {
+  b747_cfg cfg;
+  DevCfg dc;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  StateF64 s64{};
+  StateF32 s32{};
+  // staging for b747_step_host
+  void *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_term = nullptr;
+  uint8_t* d_done = nullptr;
+  b747_episode* d_eps = nullptr;
+  int64_t launches = 0;
+  size_t elem() const { return cfg.dtype == B747_F64 ? 8 : 4; }
+};
+
+extern "C" const char* b747_last_error(void) { return g_err.c_str(); }
+extern "C" int b747_obs_dim(int obs_type) { return obs_dim_of(obs_type); }
+
+extern "C" int64_t b747_done_tick(double tk) {
+  if (!(tk == tk) || isinf(tk)) return tk < 0 ? 0 : INT64_MAX;
+  if (tk <= 0) return 0;
+  int64_t n = (int64_t)floor(tk / 0.01) - 2;
+  if (n < 0) n = 0;
+  while (!((double)n * 0.01 >= tk)) n++;
+  return n;
+}
+
+extern "C" void b747_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox4x32(ctr, key, out);
+}
+
+// ---- field table -----------------------------------------------------------------------------
+namespace {
+enum FieldKind { FK_SLOT, FK_STATE0, FK_SIG, FK_TICK, FK_FLAGS, FK_EPIDX, FK_LASTRET, FK_LASTLEN, FK_MXONLY };
+struct FieldDesc { const char* name; FieldKind kind; int row; };
+const std::vector<FieldDesc>& fields() {
+  static std::vector<FieldDesc> f;
+  static std::once_flag once;
+  std::call_once(once, [] {
+#define X(n) f.push_back({#n, FK_SLOT, S_##n});
+    B747_F64_SLOTS(X)
+#undef X
+    static const char* s0n[6] = {"state0_x", "state0_y", "state0_Vx", "state0_Vy", "state0_vartheta", "state0_wz"};
+    for (int k = 0; k < 6; k++) f.push_back({s0n[k], FK_STATE0, k});
+#define X(n) f.push_back({"sig_" #n, FK_SIG, SIG_##n});
+    B747_SIGNALS(X)
+#undef X
+    f.push_back({"tick", FK_TICK, 0});
+    f.push_back({"flags", FK_FLAGS, 0});
+    f.push_back({"ep_idx", FK_EPIDX, 0});
+    f.push_back({"last_ret", FK_LASTRET, 0});
+    f.push_back({"last_len", FK_LASTLEN, 0});
+    f.push_back({"th", FK_MXONLY, 0});  // f32 handles carry the pitch angle itself instead of (q0, q3)
+  });
+  return f;
+}
+}  // namespace
+
+extern "C" int b747_n_fields(void) { return (int)fields().size(); }
+extern "C" const char* b747_field_name(int i) { return (i >= 0 && i < (int)fields().size()) ? fields()[i].name : nullptr; }
+extern "C" int b747_field_index(const char* name) {
+  const auto& f = fields();
+  for (size_t i = 0; i < f.size(); i++)
+    if (!strcmp(f[i].name, name)) return (int)i;
+  return -1;
+}
+
+// ---- lifecycle -------------------------------------------------------------------------------
+static int fill_devcfg(const b747_cfg& c, DevCfg& d) {
+  memset(&d, 0, sizeof d);
+  d.n_envs = c.n_envs;
+  d.n_pad = (c.n_envs + 127) / 128 * 128;
+  d.obs_type = c.obs_type; d.obs_dim = obs_dim_of(c.obs_type); d.rew_type = c.rew_type;
+  d.ctrl_type = c.ctrl_type; d.ctrl_mode = c.ctrl_mode; d.reset_ref_mode = c.reset_ref_mode;
+  d.disturbance_mode = c.disturbance_mode; d.norm_obs = c.norm_obs; d.norm_act = c.norm_act;
+  d.use_limiter = c.use_limiter; d.substeps = c.substeps; d.auto_reset = c.auto_reset; d.env_layer = c.env_layer;
+  d.has_fixed_aero_err = c.has_fixed_aero_err; d.done_tick = c.done_tick; d.env_id_offset = c.env_id_offset;
+  d.seed = c.seed; d.tk = c.tk; d.action_max = c.action_max; d.vartheta_max = c.vartheta_max;
+  d.sample_time = c.sample_time;
+  memcpy(d.rew, c.rew, sizeof d.rew);
+  memcpy(d.fixed_aero_err, c.fixed_aero_err, sizeof d.fixed_aero_err);
+  const double pid_cs[4] = B747_DEF_PID_CS, pid_ss[4] = B747_DEF_PID_SS;
+  memcpy(d.mp.PID_CS, pid_cs, sizeof pid_cs); memcpy(d.mp.PID_SS, pid_ss, sizeof pid_ss);
+  d.mp.P = B747_DEF_P; d.mp.Iz = B747_DEF_IZ; d.mp.S = B747_DEF_S; d.mp.c_ = B747_DEF_C; d.mp.g = B747_DEF_G;
+  d.mp.m0 = B747_DEF_M0; d.mp.use_RP = 1.0; d.mp.use_RL = B747_DEF_USE_RL;
+  // Controller._init_model (core/controller.py:128-131): use_PID_SS = not manual_stab
+  bool manual = c.ctrl_type == B747_CTRL_MANUAL || c.ctrl_type == B747_CTRL_SEMI_MANUAL;
+  d.mp.use_PID_SS = manual ? 0.0 : 1.0;
+  return 0;
+}
+
+extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
+  if (!cfg || !out) return fail(B747_ERR_ARG, "null argument");
+  if (cfg->abi_version != B747_ABI_VERSION) return fail(B747_ERR_ARG, "abi_version mismatch");
+  if (cfg->n_envs <= 0) return fail(B747_ERR_ARG, "n_envs must be > 0");
+  if (cfg->dtype != B747_F64 && cfg->dtype != B747_F32) return fail(B747_ERR_ARG, "dtype must be B747_F64 or B747_F32");
+  if (obs_dim_of(cfg->obs_type) < 0) return fail(B747_ERR_ARG, "unknown obs_type");
+  if (cfg->rew_type < 0 || cfg->rew_type > 4) return fail(B747_ERR_ARG, "unknown rew_type");
+  if (cfg->ctrl_type < 0 || cfg->ctrl_type > 3) return fail(B747_ERR_ARG, "unknown ctrl_type");
+  if (cfg->ctrl_mode < 0 || cfg->ctrl_mode > 3) return fail(B747_ERR_ARG, "unknown ctrl_mode");
+  if (cfg->reset_ref_mode < -1 || cfg->reset_ref_mode > 2) return fail(B747_ERR_ARG, "unknown reset_ref_mode");
+  if (cfg->substeps < 1) return fail(B747_ERR_ARG, "substeps must be >= 1");
+  if (cfg->dtype == B747_F32 && !cfg->env_layer)
+    return fail(B747_ERR_ARG, "env_layer=0 (raw Model stepping) needs dtype B747_F64");
+  // the reference asserts this in Controller.reset (core/controller.py:145)
+  if (cfg->reset_ref_mode != B747_RESET_NONE && cfg->env_layer &&
+      !(cfg->ctrl_type == B747_CTRL_SEMI_MANUAL || cfg->ctrl_type == B747_CTRL_MANUAL))
+    return fail(B747_ERR_ARG, "random reset needs the NN in the stabilisation loop (MANUAL / SEMI_MANUAL)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(B747_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                                   " (libb747_b200 has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(B747_ERR_ARG, "device ordinal out of range");
+  CU(cudaSetDevice(cfg->device));
+  b747_handle* h = new b747_handle();
+  h->cfg = *cfg;
+  fill_devcfg(*cfg, h->dc);
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  const size_t np = (size_t)h->dc.n_pad;
+  const int od = h->dc.obs_dim;
+  if (cfg->dtype == B747_F64) {
+    StateF64& s = h->s64;
+    CU(cudaMalloc(&s.slots, sizeof(double) * np * (NSLOT_F64 + 6)));
+    CU(cudaMalloc(&s.tick, sizeof(int) * np));
+    CU(cudaMalloc(&s.flags, sizeof(int) * np));
+    CU(cudaMalloc(&s.ep_idx, sizeof(uint32_t) * np));
+    if (cfg->export_signals) CU(cudaMalloc(&s.sig, sizeof(double) * np * NSIG));
+    CU(cudaMalloc(&s.stats, sizeof(double) * 4));
+    CU(cudaMalloc(&s.last_ret, sizeof(double) * np));
+    CU(cudaMalloc(&s.last_len, sizeof(int) * np));
+    CU(cudaMemsetAsync(s.slots, 0, sizeof(double) * np * (NSLOT_F64 + 6), h->stream));
+    CU(cudaMemsetAsync(s.stats, 0, sizeof(double) * 4, h->stream));
+    launch_defaults64(h->dc, s, h->stream);
+    h->launches++;
+  } else {
+    int rc = f32_alloc(h->dc, h->s32, cfg->export_signals != 0, h->stream);
+    if (rc) return fail(B747_ERR_CUDA, std::string("f32 state allocation: ") + cudaGetErrorString(cudaGetLastError()));
+    launch_defaults32(h->dc, h->s32, h->stream);
+    h->launches++;
+  }
+  CU(cudaMalloc(&h->d_act, h->elem() * np));
+  CU(cudaMalloc(&h->d_obs, h->elem() * np * od));
+  CU(cudaMalloc(&h->d_rew, h->elem() * np));
+  CU(cudaMalloc(&h->d_term, h->elem() * np * od));
+  CU(cudaMalloc(&h->d_done, np));
+  CU(cudaMalloc(&h->d_eps, sizeof(b747_episode) * np));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return B747_OK;
+}
+
+extern "C" int b747_destroy(b747_handle* h) {
+  if (!h) return B747_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  StateF64& s = h->s64;
+  cudaFree(s.slots); cudaFree(s.tick); cudaFree(s.flags); cudaFree(s.ep_idx); cudaFree(s.sig); cudaFree(s.stats);
+  cudaFree(s.last_ret); cudaFree(s.last_len);
+  f32_free(h->s32);
+  cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_done); cudaFree(h->d_eps);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return B747_OK;
+}
+
+extern "C" void* b747_stream(b747_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int b747_set_stream(b747_handle* h, void* s) {
+  if (!h) return fail(B747_ERR_ARG, "null handle");
+  cudaStreamSynchronize(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)s;
+  h->own_stream = false;
+  return B747_OK;
+}
+extern "C" int64_t b747_launch_count(b747_handle* h) { return h ? h->launches : 0; }
+extern "C" int b747_synchronize(b747_handle* h) {
+  if (!h) return fail(B747_ERR_ARG, "null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  return B747_OK;
+}
+
+// ---- reset / step ----------------------------------------------------------------------------
+extern "C" int b747_reset(b747_handle* h, const uint8_t* mask_dev, void* obs_dev) {
+  if (!h) return fail(B747_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.dtype == B747_F64) launch_reset64(h->dc, h->s64, mask_dev, nullptr, (double*)obs_dev, h->stream);
+  else launch_reset32(h->dc, h->s32, mask_dev, nullptr, (float*)obs_dev, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  return B747_OK;
+}
+
+extern "C" int b747_reset_to(b747_handle* h, const b747_episode* eps, void* obs_dev) {
+  if (!h || !eps) return fail(B747_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(h->d_eps, eps, sizeof(b747_episode) * h->cfg.n_envs, cudaMemcpyHostToDevice, h->stream));
+  if (h->cfg.dtype == B747_F64) launch_reset64(h->dc, h->s64, nullptr, h->d_eps, (double*)obs_dev, h->stream);
+  else launch_reset32(h->dc, h->s32, nullptr, h->d_eps, (float*)obs_dev, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));  // eps is caller memory
+  return B747_OK;
+}
+
+extern "C" int b747_step(b747_handle* h, const void* act, void* obs, void* rew, uint8_t* done, void* term) {
+  if (!h || !act || !obs || !rew || !done) return fail(B747_ERR_ARG, "null argument");
+  if (!h->cfg.env_layer) return fail(B747_ERR_STATE, "handle was created with env_layer=0; use b747_model_step");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.dtype == B747_F64)
+    launch_env_step64(h->dc, h->s64, (const double*)act, (double*)obs, (double*)rew, done, (double*)term, h->stream);
+  else
+    launch_env_step32(h->dc, h->s32, (const float*)act, (float*)obs, (float*)rew, done, (float*)term, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  return B747_OK;
+}
+
+extern "C" int b747_step_host(b747_handle* h, const void* act, void* obs, void* rew, uint8_t* done, void* term) {
+  if (!h || !act || !obs || !rew || !done) return fail(B747_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->cfg.n_envs, es = h->elem(), od = (size_t)h->dc.obs_dim;
+  CU(cudaMemcpyAsync(h->d_act, act, es * n, cudaMemcpyHostToDevice, h->stream));
+  int rc = b747_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, term ? h->d_term : nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(obs, h->d_obs, es * n * od, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(rew, h->d_rew, es * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(done, h->d_done, n, cudaMemcpyDeviceToHost, h->stream));
+  if (term) CU(cudaMemcpyAsync(term, h->d_term, es * n * od, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B747_OK;
+}
+
+extern "C" int b747_model_step(b747_handle* h, int32_t n_steps) {
+  if (!h || n_steps < 0) return fail(B747_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.dtype != B747_F64) return fail(B747_ERR_STATE, "raw model stepping needs an f64 handle (the reference's real_T is double)");
+  launch_model_step64(h->dc, h->s64, n_steps, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  return B747_OK;
+}
+
+extern "C" int b747_model_initialize(b747_handle* h) {
+  if (!h) return fail(B747_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.dtype != B747_F64) return fail(B747_ERR_STATE, "raw model stepping needs an f64 handle (the reference's real_T is double)");
+  launch_model_init64(h->dc, h->s64, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  return B747_OK;
+}
+
+// ---- uniform model parameters ----------------------------------------------------------------
+static double* param_ptr(ModelParams& mp, const char* name, int& n) {
+  n = 1;
+  if (!strcmp(name, "PID_SS")) { n = 4; return mp.PID_SS; }
+  if (!strcmp(name, "PID_CS")) { n = 4; return mp.PID_CS; }
+  if (!strcmp(name, "P")) return &mp.P;
+  if (!strcmp(name, "Iz")) return &mp.Iz;
+  if (!strcmp(name, "S")) return &mp.S;
+  if (!strcmp(name, "c_")) return &mp.c_;
+  if (!strcmp(name, "g")) return &mp.g;
+  if (!strcmp(name, "m0")) return &mp.m0;
+  if (!strcmp(name, "use_RP")) return &mp.use_RP;
+  if (!strcmp(name, "use_RL")) return &mp.use_RL;
+  if (!strcmp(name, "use_PID_SS")) return &mp.use_PID_SS;
+  return nullptr;
+}
+extern "C" int b747_set_param(b747_handle* h, const char* name, const double* v, int n) {
+  if (!h || !name || !v) return fail(B747_ERR_ARG, "null argument");
+  int len;
+  double* p = param_ptr(h->dc.mp, name, len);
+  if (!p || n != len) return fail(B747_ERR_ARG, std::string("unknown parameter or wrong length: ") + name);
+  memcpy(p, v, sizeof(double) * len);
+  return B747_OK;
+}
+extern "C" int b747_get_param(b747_handle* h, const char* name, double* v, int n) {
+  if (!h || !name || !v) return fail(B747_ERR_ARG, "null argument");
+  int len;
+  double* p = param_ptr(h->dc.mp, name, len);
+  if (!p || n != len) return fail(B747_ERR_ARG, std::string("unknown parameter or wrong length: ") + name);
+  memcpy(v, p, sizeof(double) * len);
+  return B747_OK;
+}
+
+// ---- per-env fields ---------------------------------------------------------------------------
+static int field_io(b747_handle* h, int field, double* out, const double* in) {
+  if (!h || field < 0 || field >= (int)fields().size()) return fail(B747_ERR_ARG, "bad field");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const FieldDesc& f = fields()[field];
+  const size_t n = (size_t)h->cfg.n_envs, np = (size_t)h->dc.n_pad;
+  if (h->cfg.dtype == B747_F32) return f32_field_io(h->dc, h->s32, (int)f.kind, f.row, f.name, out, in, h->stream) ? fail(B747_ERR_ARG, std::string("field not available on an f32 handle: ") + f.name) : B747_OK;
+  StateF64& s = h->s64;
+  std::vector<int> tmp;
+  auto io_double = [&](double* dev) -> int {
+    if (out) CU(cudaMemcpy(out, dev, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    else CU(cudaMemcpy(dev, in, sizeof(double) * n, cudaMemcpyHostToDevice));
+    return B747_OK;
+  };
+  auto io_int = [&](int* dev) -> int {
+    tmp.resize(n);
+    if (out) {
+      CU(cudaMemcpy(tmp.data(), dev, sizeof(int) * n, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; i++) out[i] = (double)tmp[i];
+    } else {
+      for (size_t i = 0; i < n; i++) tmp[i] = (int)in[i];
+      CU(cudaMemcpy(dev, tmp.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    }
+    return B747_OK;
+  };
+  switch (f.kind) {
+    case FK_SLOT: return io_double(s.slots + (size_t)f.row * np);
+    case FK_STATE0: return io_double(s.slots + (size_t)(NSLOT_F64 + f.row) * np);
+    case FK_SIG:
+      if (!s.sig) return fail(B747_ERR_STATE, "handle was created without export_signals");
+      return io_double(s.sig + (size_t)f.row * np);
+    case FK_TICK: return io_int(s.tick);
+    case FK_FLAGS: return io_int(s.flags);
+    case FK_EPIDX: return io_int((int*)s.ep_idx);
+    case FK_LASTRET: return io_double(s.last_ret);
+    case FK_LASTLEN: return io_int(s.last_len);
+    case FK_MXONLY: return fail(B747_ERR_ARG, std::string("field only exists on f32 handles: ") + f.name);
+  }
+  return fail(B747_ERR_ARG, "bad field kind");
+}
+extern "C" int b747_get_field(b747_handle* h, int field, double* out) {
+  if (!out) return fail(B747_ERR_ARG, "null argument");
+  return field_io(h, field, out, nullptr);
+}
+extern "C" int b747_set_field(b747_handle* h, int field, const double* in) {
+  if (!in) return fail(B747_ERR_ARG, "null argument");
+  return field_io(h, field, nullptr, in);
+}
+
+// ---- episode statistics -----------------------------------------------------------------------
+extern "C" int b747_episode_stats(b747_handle* h, double out[4]) {
+  if (!h || !out) return fail(B747_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  double* st = h->cfg.dtype == B747_F64 ? h->s64.stats : h->s32.stats;
+  CU(cudaMemcpyAsync(out, st, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemsetAsync(st, 0, sizeof(double) * 4, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B747_OK;
+}
+
+extern "C" int b747_last_episode(b747_handle* h, double* ret, int32_t* len) {
+  if (!h || !ret || !len) return fail(B747_ERR_ARG, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t n = (size_t)h->cfg.n_envs;
+  if (h->cfg.dtype == B747_F64) {
+    CU(cudaMemcpy(ret, h->s64.last_ret, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(len, h->s64.last_len, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  } else {
+    CU(cudaMemcpy(ret, h->s32.last_ret, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(len, h->s32.last_len, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  }
+  return B747_OK;
+}

@@ -1,0 +1,498 @@
+// b747_kernels_f32.cu -- throughput kernels ("f32" handles): ControllerEnv.step for every env in one
+// launch, one env per thread, K fused RK4 substeps with the state in registers
+// (replaces env/ctrl_env.py:260-270 -> core/controller.py:231-264 -> model_simple_step dll@0x16d0 xK).
+//
+// HBM layout (per handle): field groups of 16 bytes per env, group-major --
+//   D[g][env] : double2   g = 0:(h,th) 1:(Vx,Vy) 2:(wz,ssi) 3:(ssf,dvi) 4:(itse,d1_u) 5:(vref,ep_return)
+//                             6:(csi,csf) 7:(x,href) 8..10: oscillating-reference (A0,A1)(A2,f0)(f1,f2)
+//                             11..13: state0
+//   F[g][env] : float4    g = 0:(df_x,df_y,rl_prev,deltaz) 1:(uh0..uh3) 2:(sig_upid,d2_u,tick,flags|episode<<8)
+//                             3:(sumA0..3) 4:(sumA4,tf_tp,sig_vzh,-)
+// so each thread moves its state with 128-bit loads/stores and a warp touches one contiguous 512-byte
+// segment per group.  The canonical configuration (LEAN) reads and writes groups D0-5 and F0-2 only:
+// 144 B in + 144 B out per env step, plus action (4) obs (12) reward (4) done (1) = 309 B/env-step,
+// independent of K.
+#include <string.h>
+
+#include <vector>
+
+#include "b747_kernels.h"
+#include "b747_model_mx.cuh"
+
+namespace b747 {
+
+enum { DG_h_th = 0, DG_V, DG_wz_ssi, DG_ssf_dvi, DG_itse_d1, DG_vref_ret, DG_cs, DG_x_href, DG_osc0, DG_osc1, DG_osc2,
+       DG_s0a, DG_s0b, DG_s0c, ND_GROUPS };
+enum { FG_act = 0, FG_uh, FG_misc, FG_sumA, FG_misc2, NF_GROUPS };
+
+template <bool GEN>
+__device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, RegsMx& r) {
+  const double2* __restrict__ D = st.D;
+  const float4* __restrict__ F = st.F;
+  double2 d;
+  d = D[DG_h_th * np + i]; r.h = d.x; r.th = d.y;
+  d = D[DG_V * np + i]; r.Vx = d.x; r.Vy = d.y;
+  d = D[DG_wz_ssi * np + i]; r.wz = d.x; r.ssi = d.y;
+  d = D[DG_ssf_dvi * np + i]; r.ssf = d.x; r.dvi = d.y;
+  d = D[DG_itse_d1 * np + i]; r.itse = d.x; r.d1_u = d.y;
+  d = D[DG_vref_ret * np + i]; r.vref = d.x; r.ep_return = d.y;
+  float4 f;
+  f = F[FG_act * np + i]; r.df_x = f.x; r.df_y = f.y; r.rl_prev = f.z; r.deltaz = f.w;
+  f = F[FG_uh * np + i]; r.uh[0] = f.x; r.uh[1] = f.y; r.uh[2] = f.z; r.uh[3] = f.w;
+  f = F[FG_misc * np + i]; r.sig_upid = f.x; r.d2_u = f.y; r.tick = __float_as_int(f.z);
+  const unsigned fw = __float_as_uint(f.w);
+  r.flags = (int)(fw & 0xffu); r.ep_idx = fw >> 8;
+  if (GEN) {
+    d = D[DG_cs * np + i]; r.csi = d.x; r.csf = d.y;
+    d = D[DG_x_href * np + i]; r.x = d.x; r.href = d.y;
+    d = D[DG_osc0 * np + i]; r.oscA[0] = d.x; r.oscA[1] = d.y;
+    d = D[DG_osc1 * np + i]; r.oscA[2] = d.x; r.oscf[0] = d.y;
+    d = D[DG_osc2 * np + i]; r.oscf[1] = d.x; r.oscf[2] = d.y;
+    f = F[FG_sumA * np + i]; r.sumA[0] = f.x; r.sumA[1] = f.y; r.sumA[2] = f.z; r.sumA[3] = f.w;
+    f = F[FG_misc2 * np + i]; r.sumA[4] = f.x; r.tf_tp = f.y; r.sig_vzh = f.z;
+  } else {
+    r.csi = r.csf = r.x = 0.0; r.href = B747_DEF_H_ZH;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { r.oscA[k] = 0.0; r.oscf[k] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < 5; k++) r.sumA[k] = 1.0f;
+    r.tf_tp = 0.f; r.sig_vzh = 0.f;
+  }
+  r.vartheta = 0.0;
+}
+
+// `full`: also the groups a step never changes (reference, aero sums, state0) -- reset paths only.
+template <bool GEN>
+__device__ __forceinline__ void store_mx(const StateF32& st, size_t np, int i, const RegsMx& r, bool full) {
+  double2* __restrict__ D = st.D;
+  float4* __restrict__ F = st.F;
+  D[DG_h_th * np + i] = make_double2(r.h, r.th);
+  D[DG_V * np + i] = make_double2(r.Vx, r.Vy);
+  D[DG_wz_ssi * np + i] = make_double2(r.wz, r.ssi);
+  D[DG_ssf_dvi * np + i] = make_double2(r.ssf, r.dvi);
+  D[DG_itse_d1 * np + i] = make_double2(r.itse, r.d1_u);
+  D[DG_vref_ret * np + i] = make_double2(r.vref, r.ep_return);
+  F[FG_act * np + i] = make_float4(r.df_x, r.df_y, r.rl_prev, r.deltaz);
+  F[FG_uh * np + i] = make_float4(r.uh[0], r.uh[1], r.uh[2], r.uh[3]);
+  F[FG_misc * np + i] = make_float4(r.sig_upid, r.d2_u, __int_as_float(r.tick),
+                                    __uint_as_float(((unsigned)r.flags & 0xffu) | (r.ep_idx << 8)));
+  if (GEN) {
+    D[DG_cs * np + i] = make_double2(r.csi, r.csf);
+    D[DG_x_href * np + i] = make_double2(r.x, r.href);
+    F[FG_misc2 * np + i] = make_float4(r.sumA[4], r.tf_tp, r.sig_vzh, 0.f);
+    if (full) {
+      D[DG_osc0 * np + i] = make_double2(r.oscA[0], r.oscA[1]);
+      D[DG_osc1 * np + i] = make_double2(r.oscA[2], r.oscf[0]);
+      D[DG_osc2 * np + i] = make_double2(r.oscf[1], r.oscf[2]);
+      F[FG_sumA * np + i] = make_float4(r.sumA[0], r.sumA[1], r.sumA[2], r.sumA[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_state0_mx(const StateF32& st, size_t np, int i, const double s0[6]) {
+  st.D[DG_s0a * np + i] = make_double2(s0[0], s0[1]);
+  st.D[DG_s0b * np + i] = make_double2(s0[2], s0[3]);
+  st.D[DG_s0c * np + i] = make_double2(s0[4], s0[5]);
+}
+
+template <bool GEN>
+__device__ __forceinline__ void env_reset_mx(const DevCfg& c, const Episode& ep, RegsMx& r, const StateF32& st, size_t np,
+                                             int i) {
+  int use_ctrl = (c.ctrl_type == B747_CTRL_SEMI_MANUAL || c.ctrl_type == B747_CTRL_FULL_AUTO);
+  if (c.reset_ref_mode == B747_RESET_HYBRID) {
+    use_ctrl = ep.use_ctrl;
+#pragma unroll
+    for (int k = 0; k < 5; k++) r.sumA[k] = 1.0f;
+  }
+  r.flags = (use_ctrl ? FL_USE_CTRL : 0) | (ep.osc ? FL_OSC : 0);
+  if (c.disturbance_mode == B747_DIST_AERO) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) r.sumA[k] = (float)(ep.aerr[k] + 1.0);
+  }
+  model_init32(ep.s0, r);
+  r.vref = ep.vref; r.href = ep.href;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { r.oscA[k] = ep.oscA[k]; r.oscf[k] = ep.oscf[k]; }
+  r.ep_return = 0.0;
+  r.vartheta = 0.0;
+  if (GEN) store_state0_mx(st, np, i, ep.s0);
+}
+
+__device__ __forceinline__ void episode_from_state_mx(const StateF32& st, size_t np, int i, const RegsMx& r, Episode& ep) {
+  double2 d;
+  d = st.D[DG_s0a * np + i]; ep.s0[0] = d.x; ep.s0[1] = d.y;
+  d = st.D[DG_s0b * np + i]; ep.s0[2] = d.x; ep.s0[3] = d.y;
+  d = st.D[DG_s0c * np + i]; ep.s0[4] = d.x; ep.s0[5] = d.y;
+  ep.vref = r.vref; ep.href = r.href;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ep.oscA[k] = r.oscA[k]; ep.oscf[k] = r.oscf[k]; }
+#pragma unroll
+  for (int k = 0; k < 5; k++) ep.aerr[k] = (double)r.sumA[k] - 1.0;
+  ep.use_ctrl = (r.flags & FL_USE_CTRL) != 0;
+  ep.osc = (r.flags & FL_OSC) != 0;
+}
+
+__device__ __forceinline__ float nan_to_num_f(float x) {
+  if (x != x) return 0.f;
+  if (isinf(x)) return x > 0 ? 3.402823466e38f : -3.402823466e38f;
+  return x;
+}
+
+__device__ __forceinline__ void load_tables32(float* sP, float* sR) {
+  static const __device__ double gP[kNP] = B747_P_INIT;
+  for (int k = threadIdx.x; k < kNP; k += blockDim.x) {
+    sP[k] = (float)gP[k];
+    sR[k] = (k + 1 < kNP) ? (float)(1.0 / (gP[k + 1] - gP[k])) : 0.f;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
+                                                    float* __restrict__ obs_out, float* __restrict__ rew_out,
+                                                    uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
+  __shared__ float sP[kNP];
+  __shared__ float sR[kNP];
+  __shared__ EpStatsSmem sst;
+  load_tables32(sP, sR);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < c.n_envs;
+  const size_t np = (size_t)c.n_pad;
+  bool done = false;
+  double ep_ret = 0.0, ep_len = 0.0;
+  if (live) {
+    RegsMx r;
+    load_mx<GEN>(st, np, i, r);
+    float a = actions[i];
+    if (c.norm_act) a *= (float)c.action_max;
+    const bool use_ctrl = GEN && (r.flags & FL_USE_CTRL);
+    // Controller.step: reference, then the action law (core/controller.py:233-251)
+    if (!use_ctrl) {
+      if (GEN && (r.flags & FL_OSC)) {
+        const double time0 = (double)r.tick * kH;
+        r.vartheta = r.oscA[0] * sin(2 * kPi * r.oscf[0] * time0) + r.oscA[1] * sin(2 * kPi * r.oscf[1] * time0) +
+                     r.oscA[2] * sin(2 * kPi * r.oscf[2] * time0);
+      } else {
+        r.vartheta = r.vref;
+      }
+    }
+    if (!(mp.use_PID_SS != 0.f)) {
+      const float lim = (float)(17 * kPi / 180);
+      float dz;
+      switch (c.ctrl_mode) {
+        case B747_MODE_ADD_PROC: dz = satf((1.f + a) * r.sig_upid, -lim, lim); break;
+        case B747_MODE_ADD_DIRECT: dz = satf(a + r.sig_upid, -lim, lim); break;
+        case B747_MODE_ANG_VEL: dz = satf(fmaf(a, (float)c.sample_time, r.deltaz), -lim, lim); break;
+        default: dz = a; break;
+      }
+      r.deltaz = dz;
+    }
+    PassMx o;
+    Stage4Mx s4;
+    const bool want_x = GEN && c.obs_type == B747_OBS_MODEL_STATE;
+#pragma unroll 1
+    for (int k = 0; k < c.substeps; k++) model_step32<GEN>(sP, sR, mp, c, r, o, s4, want_x);
+    r.sig_upid = o.U_com_PID; r.sig_vzh = o.vartheta_zh;
+    // stage-4 Derivative-block signals (float64 differences of the pitch error)
+    const double dv_dt = (o.dv - r.d1_u) * 100.0;
+    const float dv_dt_f = (float)dv_dt;
+    const float dv_dt_dt = (dv_dt_f - r.d2_u) * 100.0f;
+    const float dv = (float)o.dv;
+    const float time = (float)((double)r.tick * kH);
+    // Controller.vartheta_ref (core/controller.py:267-270)
+    const float vr = use_ctrl ? r.sig_vzh : (float)r.vartheta;
+    // observation (env/ctrl_env.py:200-247)
+    float obs[10];
+    int od = c.obs_dim;
+    {
+      const float pi = (float)kPi;
+      if (c.obs_type == B747_OBS_MODEL_STATE) {
+        obs[0] = vr; obs[1] = nan_to_num_f(s4.x); obs[2] = nan_to_num_f(s4.h); obs[3] = nan_to_num_f(s4.Vx);
+        obs[4] = nan_to_num_f(s4.Vy); obs[5] = nan_to_num_f(o.th); obs[6] = nan_to_num_f(s4.wz);
+        if (c.norm_obs) {
+          obs[0] /= (float)(10 * kPi / 180); obs[1] /= 12000.f; obs[2] /= 15000.f; obs[3] /= 500.f; obs[4] /= 100.f;
+          obs[5] /= pi; obs[6] /= pi;
+        }
+      } else {
+        float mx[10];
+        int n = 3;
+        obs[0] = (float)s4.dvi; obs[1] = dv; obs[2] = dv_dt_f;
+        mx[0] = (float)(60 * kPi); mx[1] = pi; mx[2] = pi;
+        if (c.obs_type == B747_OBS_SPEED_MODE || c.obs_type == B747_OBS_PID_SPEED_AERO) {
+          obs[n] = nan_to_num_f(s4.Vx); mx[n++] = 500.f;
+          obs[n] = nan_to_num_f(s4.Vy); mx[n++] = 100.f;
+        }
+        if (c.obs_type == B747_OBS_PID_AERO || c.obs_type == B747_OBS_PID_SPEED_AERO) {
+          obs[n] = o.CXa; mx[n++] = 0.5f; obs[n] = o.CYa; mx[n++] = 2.f; obs[n] = o.mz; mx[n++] = 0.6f;
+          obs[n] = o.dCm; mx[n++] = 0.05f; obs[n] = o.K_alpha; mx[n++] = 1.f;
+        }
+        if (c.norm_obs)
+          for (int k = 0; k < n; k++) obs[k] /= mx[k];
+      }
+    }
+    // reward (env/ctrl_env.py:109-192)
+    float rew = 0.f;
+    {
+      const float vf = vr != 0.f ? vr : (float)c.vartheta_max;
+      const float itse = (float)s4.itse;
+      switch (c.rew_type) {
+        case B747_REW_CLASSIC: {
+          const float k1 = (float)c.rew[0], k2 = (float)c.rew[1], k3 = (float)c.rew[2], k0 = (float)c.rew[3],
+                      kI = (float)c.rew[4], kf = (float)c.rew[5], kt = (float)c.rew[6], ko = (float)c.rew[7];
+          const float inv_vf = 1.0f / vf;
+          const float rel = fabsf(dv * inv_vf);
+          float r1 = 0.5f * expf(-k0 * (k1 * fabsf(dv) + k2 * fabsf(dv_dt_f) + k3 * fabsf(dv_dt_dt)) * fabsf(inv_vf));
+          float r2 = (vr * dv < 0.f) ? 0.2f * expf(-ko * rel) : 0.2f;
+          float r3 = (rel > 0.05f) ? 0.2f * expf(-kt * time) : 0.2f;
+          float r4 = 0.1f * expf(-kI * itse * inv_vf * inv_vf);
+          float rf = 0.f;
+          if (c.ctrl_mode == B747_MODE_DIRECT)
+            rf = -kf * (0.5f * rel) * fabsf(r.deltaz - o.U_com_PID) * (float)(1.0 / (34 * kPi / 180));
+          rew = r1 + r2 + r3 + r4 + rf;
+          break;
+        }
+        case B747_REW_PID_LIKE:
+          rew = expf(-(float)c.rew[0] * fabsf(o.U_com - o.U_com_PID) * (float)(1.0 / (34 * kPi / 180)));
+          break;
+        case B747_REW_QUALITY:
+        case B747_REW_MINIMAL:
+          rew = expf(-6.0f * itse / ((float)c.tk * (vr * vr)));
+          break;
+        case B747_REW_TF_REFERENCE: {
+          float overshoot = fabsf(dv / vf) * 100.f;
+          if (overshoot > 5.f) r.tf_tp = time;
+          rew = expf(-(float)c.rew[2] * fabsf(overshoot - (float)c.rew[0]) * fabsf((float)c.rew[1] - r.tf_tp));
+          break;
+        }
+      }
+    }
+    r.ep_return += (double)rew;
+    done = (int64_t)r.tick >= c.done_tick;
+    if (c.use_limiter && (fabsf(nan_to_num_f(o.th)) > (float)(5 * kPi / 180 + c.vartheta_max) || r.deltaz > (float)c.action_max))
+      done = true;
+    if (st.sig) {
+      float* sg = st.sig;
+#define SG(name, v) sg[(size_t)SIG_##name * np + i] = (v)
+      const float qn = nanf("");
+      SG(state_x, s4.x); SG(state_y, s4.h); SG(state_Vx, s4.Vx); SG(state_Vy, s4.Vy); SG(state_vartheta, o.th);
+      SG(state_wz, s4.wz); SG(sim_time, time); SG(vartheta_zh, o.vartheta_zh); SG(U_com_PID, o.U_com_PID);
+      SG(CXa, o.CXa); SG(CYa, o.CYa); SG(mz, o.mz); SG(K_alpha, o.K_alpha); SG(dCm_ddeltaz, o.dCm); SG(U_com, o.U_com);
+      SG(deltaz_RP, o.deltaz_RP); SG(dvartheta, dv); SG(dvartheta_int, (float)s4.dvi); SG(dvartheta_dt, dv_dt_f);
+      SG(dvartheta_dt_dt, dv_dt_dt); SG(TAE, fabsf(dv) * time); SG(ITAE, qn); SG(TSE, dv * dv * time);
+      SG(ITSE, (float)s4.itse); SG(AE, fabsf(dv)); SG(IAE, qn); SG(SE, dv * dv); SG(ISE, qn); SG(alpha, o.alpha);
+      SG(V, o.V); SG(Mach, o.Mach);
+#undef SG
+    }
+    rew_out[i] = rew;
+    done_out[i] = done ? 1 : 0;
+    if (term_obs)
+      for (int k = 0; k < od; k++) term_obs[(size_t)i * od + k] = obs[k];
+    bool full_store = false;
+    if (done) {
+      ep_ret = r.ep_return; ep_len = (double)(r.tick / c.substeps);
+      st.last_ret[i] = ep_ret; st.last_len[i] = r.tick / c.substeps;
+      if (c.auto_reset) {
+        Episode ep;
+        if (c.reset_ref_mode == B747_RESET_NONE) episode_from_state_mx(st, np, i, r, ep);
+        else { draw_episode(c, (uint64_t)(c.env_id_offset + i), r.ep_idx, ep); r.ep_idx++; }
+        env_reset_mx<GEN>(c, ep, r, st, np, i);
+        full_store = true;
+        for (int k = 0; k < od; k++) obs[k] = 0.f;
+        if (st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
+      }
+    }
+    if (od == 3) {  // canonical layout: three contiguous floats per env
+      float* q = obs_out + (size_t)i * 3;
+      q[0] = obs[0]; q[1] = obs[1]; q[2] = obs[2];
+    } else {
+      for (int k = 0; k < od; k++) obs_out[(size_t)i * od + k] = obs[k];
+    }
+    store_mx<GEN>(st, np, i, r, full_store);
+  }
+  block_episode_stats(sst, done, ep_ret, ep_len, st.stats);
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_reset32(DevCfg c, StateF32 st, const uint8_t* __restrict__ mask,
+                                                 const b747_episode* __restrict__ eps, float* __restrict__ obs_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n_envs) return;
+  if (mask && !mask[i]) return;
+  const size_t np = (size_t)c.n_pad;
+  RegsMx r;
+  load_mx<GEN>(st, np, i, r);
+  Episode ep;
+  if (eps) {
+    const b747_episode& e = eps[i];
+    for (int k = 0; k < 6; k++) ep.s0[k] = e.state0[k];
+    ep.vref = e.vref_const; ep.href = e.h_ref; ep.use_ctrl = e.use_ctrl; ep.osc = e.oscillating;
+    for (int k = 0; k < 3; k++) { ep.oscA[k] = e.osc_A[k]; ep.oscf[k] = e.osc_f[k]; }
+    for (int k = 0; k < 5; k++) ep.aerr[k] = e.aero_err[k];
+  } else if (c.reset_ref_mode == B747_RESET_NONE) {
+    episode_from_state_mx(st, np, i, r, ep);
+  } else {
+    draw_episode(c, (uint64_t)(c.env_id_offset + i), r.ep_idx, ep);
+    r.ep_idx++;
+  }
+  env_reset_mx<GEN>(c, ep, r, st, np, i);
+  if (obs_out)
+    for (int k = 0; k < c.obs_dim; k++) obs_out[(size_t)i * c.obs_dim + k] = 0.f;
+  if (st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
+  store_mx<GEN>(st, np, i, r, true);
+}
+
+__global__ void __launch_bounds__(128) k_defaults32(DevCfg c, StateF32 st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n_pad) return;
+  const size_t np = (size_t)c.n_pad;
+  RegsMx r;
+  const double s0[6] = B747_DEF_STATE0;
+  r.flags = (c.ctrl_type == B747_CTRL_SEMI_MANUAL || c.ctrl_type == B747_CTRL_FULL_AUTO) ? FL_USE_CTRL : 0;
+  r.ep_idx = 0;
+  for (int k = 0; k < 5; k++) r.sumA[k] = 1.0f;
+  model_init32(s0, r);
+  r.vref = 0.0; r.href = B747_DEF_H_ZH; r.vartheta = 0.0;
+  for (int k = 0; k < 3; k++) { r.oscA[k] = 0.0; r.oscf[k] = 0.0; }
+  r.ep_return = 0.0; r.tf_tp = 0.f;
+  store_state0_mx(st, np, i, s0);
+  if (st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
+  st.last_ret[i] = 0.0; st.last_len[i] = 0;
+  store_mx<true>(st, np, i, r, true);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+bool f32_is_lean(const DevCfg& c) {
+  return c.ctrl_type == B747_CTRL_MANUAL && c.reset_ref_mode == B747_RESET_CONST && c.disturbance_mode == B747_DIST_NONE &&
+         c.rew_type != B747_REW_TF_REFERENCE && c.obs_type != B747_OBS_MODEL_STATE;
+}
+
+static MP32 make_mp32(const ModelParams& m) {
+  MP32 p;
+  for (int k = 0; k < 4; k++) { p.PID_SS[k] = (float)m.PID_SS[k]; p.PID_CS[k] = (float)m.PID_CS[k]; }
+  p.P = (float)m.P; p.g = (float)m.g; p.inv_m0 = (float)(1.0 / m.m0);
+  p.half_S = (float)(Pc(134) * m.S);
+  p.half_Sc_over_Iz = (float)(Pc(135) * m.S * m.c_ / m.Iz);
+  p.use_RP = (float)m.use_RP; p.use_RL = (float)m.use_RL; p.use_PID_SS = (float)m.use_PID_SS;
+  return p;
+}
+
+int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t stream) {
+  const size_t np = (size_t)c.n_pad;
+  if (cudaMalloc(&s.D, sizeof(double2) * np * ND_GROUPS) != cudaSuccess) return -1;
+  if (cudaMalloc(&s.F, sizeof(float4) * np * NF_GROUPS) != cudaSuccess) return -1;
+  if (export_signals && cudaMalloc(&s.sig, sizeof(float) * np * NSIG) != cudaSuccess) return -1;
+  if (cudaMalloc(&s.stats, sizeof(double) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&s.last_ret, sizeof(double) * np) != cudaSuccess) return -1;
+  if (cudaMalloc(&s.last_len, sizeof(int) * np) != cudaSuccess) return -1;
+  cudaMemsetAsync(s.D, 0, sizeof(double2) * np * ND_GROUPS, stream);
+  cudaMemsetAsync(s.F, 0, sizeof(float4) * np * NF_GROUPS, stream);
+  cudaMemsetAsync(s.stats, 0, sizeof(double) * 4, stream);
+  return 0;
+}
+
+void f32_free(StateF32& s) {
+  cudaFree(s.D); cudaFree(s.F); cudaFree(s.sig); cudaFree(s.stats); cudaFree(s.last_ret); cudaFree(s.last_len);
+  s = StateF32{};
+}
+
+static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
+
+void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
+                       float* term_obs, cudaStream_t s) {
+  const MP32 mp = make_mp32(c.mp);
+  if (f32_is_lean(c))
+    k_env_step32<false><<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+  else
+    k_env_step32<true><<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+}
+void launch_reset32(const DevCfg& c, const StateF32& st, const uint8_t* mask, const b747_episode* eps, float* obs,
+                    cudaStream_t s) {
+  // resets always go through the general layout so that every group is initialised
+  k_reset32<true><<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, st, mask, eps, obs);
+}
+void launch_defaults32(const DevCfg& c, const StateF32& st, cudaStream_t s) {
+  k_defaults32<<<grid_for(c.n_pad, 128), 128, 0, s>>>(c, st);
+}
+
+// Per-env fields of an f32 handle: (group, lane) lookup by name; returns non-zero if unavailable.
+namespace {
+struct MxField { const char* name; int is_f; int group; int lane; };
+const MxField kMxFields[] = {
+    {"h", 0, DG_h_th, 0}, {"th", 0, DG_h_th, 1}, {"Vx", 0, DG_V, 0}, {"Vy", 0, DG_V, 1}, {"wz", 0, DG_wz_ssi, 0},
+    {"ss_int", 0, DG_wz_ssi, 1}, {"ss_flt", 0, DG_ssf_dvi, 0}, {"dv_int", 0, DG_ssf_dvi, 1}, {"itse", 0, DG_itse_d1, 0},
+    {"d1_u", 0, DG_itse_d1, 1}, {"vref", 0, DG_vref_ret, 0}, {"ep_return", 0, DG_vref_ret, 1}, {"cs_int", 0, DG_cs, 0},
+    {"cs_flt", 0, DG_cs, 1}, {"x", 0, DG_x_href, 0}, {"href", 0, DG_x_href, 1},
+    {"df_x", 1, FG_act, 0}, {"df_y", 1, FG_act, 1}, {"rl_prev", 1, FG_act, 2}, {"deltaz", 1, FG_act, 3},
+    {"uh0", 1, FG_uh, 0}, {"uh1", 1, FG_uh, 1}, {"uh2", 1, FG_uh, 2}, {"uh3", 1, FG_uh, 3},
+    {"sig_upid", 1, FG_misc, 0}, {"d2_u", 1, FG_misc, 1}, {"tf_tp", 1, FG_misc2, 1}, {"sig_vzh", 1, FG_misc2, 2},
+};
+}  // namespace
+
+int f32_field_io(const DevCfg& c, StateF32& s, int kind, int row, const char* name, double* out, const double* in,
+                 cudaStream_t stream) {
+  const size_t n = (size_t)c.n_envs, np = (size_t)c.n_pad;
+  // kinds follow b747_capi.cu: 2 = signal, 3 = tick, 4 = flags, 5 = ep_idx, 6 = last_ret, 7 = last_len
+  if (kind == 2) {
+    if (!s.sig || in) return -1;
+    std::vector<float> tmp(n);
+    if (cudaMemcpy(tmp.data(), s.sig + (size_t)row * np, sizeof(float) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (size_t i = 0; i < n; i++) out[i] = tmp[i];
+    return 0;
+  }
+  if (kind == 6) {
+    if (in) return -1;
+    return cudaMemcpy(out, s.last_ret, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess;
+  }
+  if (kind == 7) {
+    if (in) return -1;
+    std::vector<int> tmp(n);
+    if (cudaMemcpy(tmp.data(), s.last_len, sizeof(int) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (size_t i = 0; i < n; i++) out[i] = tmp[i];
+    return 0;
+  }
+  if (kind == 3 || kind == 4 || kind == 5) {
+    std::vector<float4> tmp(n);
+    float4* dev = s.F + (size_t)FG_misc * np;
+    if (cudaMemcpy(tmp.data(), dev, sizeof(float4) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (size_t i = 0; i < n; i++) {
+      uint32_t tz, fw;
+      memcpy(&tz, &tmp[i].z, 4); memcpy(&fw, &tmp[i].w, 4);
+      if (out) out[i] = kind == 3 ? (double)(int)tz : (kind == 4 ? (double)(fw & 0xffu) : (double)(fw >> 8));
+      else {
+        if (kind == 3) tz = (uint32_t)(int)in[i];
+        else if (kind == 4) fw = (fw & ~0xffu) | ((uint32_t)in[i] & 0xffu);
+        else fw = (fw & 0xffu) | ((uint32_t)in[i] << 8);
+        memcpy(&tmp[i].z, &tz, 4); memcpy(&tmp[i].w, &fw, 4);
+      }
+    }
+    if (in && cudaMemcpy(dev, tmp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    return 0;
+  }
+  for (const MxField& f : kMxFields) {
+    if (strcmp(f.name, name)) continue;
+    if (f.is_f) {
+      std::vector<float4> tmp(n);
+      float4* dev = s.F + (size_t)f.group * np;
+      if (cudaMemcpy(tmp.data(), dev, sizeof(float4) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+      for (size_t i = 0; i < n; i++) {
+        float* p = &tmp[i].x + f.lane;
+        if (out) out[i] = *p; else *p = (float)in[i];
+      }
+      if (in && cudaMemcpy(dev, tmp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    } else {
+      std::vector<double2> tmp(n);
+      double2* dev = s.D + (size_t)f.group * np;
+      if (cudaMemcpy(tmp.data(), dev, sizeof(double2) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+      for (size_t i = 0; i < n; i++) {
+        double* p = &tmp[i].x + f.lane;
+        if (out) out[i] = *p; else *p = in[i];
+      }
+      if (in && cudaMemcpy(dev, tmp.data(), sizeof(double2) * n, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    }
+    return 0;
+  }
+  return -1;
+}
+
+}  // namespace b747

@@ -1,0 +1,48 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The CPU checker (plain-C restatement), built on demand."""
+    from oracle import oracle as O
+    O.build()
+    O.olib()
+    return O
+
+
+@pytest.fixture(scope="session")
+def dllref():
+    """The reference DLL's own machine code; only where oracle/_ref was built (needs /root/reference
+    at build time; the built .so travels to the GPU box)."""
+    from oracle import dllref as D
+    if not D.available():
+        pytest.skip("oracle/_ref/libb747_ref.so not built")
+    return D
