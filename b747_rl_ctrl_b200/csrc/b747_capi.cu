@@ -48,6 +48,15 @@ extern "C" int64_t b747_done_tick(double tk) {
   return n;
 }
 
+extern "C" int b747_abi_info(int which) {
+  switch (which) {
+    case 0: return B747_ABI_VERSION;
+    case 1: return (int)sizeof(b747_cfg);
+    case 2: return (int)sizeof(b747_episode);
+  }
+  return -1;
+}
+
 extern "C" void b747_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   philox4x32(ctr, key, out);
 }

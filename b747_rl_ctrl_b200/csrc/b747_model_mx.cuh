@@ -90,11 +90,11 @@ __device__ __forceinline__ float bilin32(const float* __restrict__ tab, int i0, 
 // constant (0.01 or 0.005), stage: 0 major, 1/2 half steps, 3 full step.
 template <bool GEN>
 __device__ __forceinline__ void pass32(const float* __restrict__ sP, const float* __restrict__ sR, const MP32& mp,
-                                       const DevCfg& c, int stage, int n, double th_d, double t_d, float h, float Vx,
-                                       float Vy, float wz, float ssi, float ssf, float csi, float csf, RegsMx& r,
-                                       bool& memout_ss, bool& memout_cs, PassMx& o, float& f_h, float& f_Vx,
-                                       float& f_Vy, float& f_wz, float& f_ssi, float& f_ssf, float& f_csi,
-                                       float& f_csf, double& f_itse) {
+                                       const DevCfg& c, int stage, int n, double th_d, double t_d, float h, double h_d,
+                                       float Vx, float Vy, float wz, float ssi, float ssf, double csi, double csf,
+                                       RegsMx& r, bool& memout_ss, bool& memout_cs, PassMx& o, float& f_h, float& f_Vx,
+                                       float& f_Vy, float& f_wz, float& f_ssi, float& f_ssf, double& f_csi,
+                                       double& f_csf, double& f_itse) {
   const bool major = stage == 0;
   // attitude: the DLL's th = asin(sin(theta)) folds beyond +-90 deg; keep that (rare) behaviour
   float thf = (float)th_d;
@@ -167,20 +167,23 @@ __device__ __forceinline__ void pass32(const float* __restrict__ sP, const float
   }
   o.rl_out = yv;
   o.deltaz_RP = satf(yv, PCF(145), PCF(144));
-  // СУ PID (altitude loop) -- only integrated when the configuration can close it
+  // СУ PID (altitude loop) -- only integrated when the configuration can close it.  Its output is the
+  // pitch reference, which the СС PID differentiates with a gain of Kd*N ~ 390, so the whole
+  // altitude-error chain is float64 (a float32 altitude quantises it at ~1e-5 rad).
   float use_cs = 0.f;
-  float cs_pre = 0.f, cs_d = 0.f, e_h = 0.f;
+  double cs_pre = 0.0, cs_d = 0.0, e_h = 0.0, vzh_d = 0.0;
   if (GEN) {
     use_cs = (r.flags & FL_USE_CTRL) ? 1.f : 0.f;
-    e_h = (float)r.href - h;  // h_zh
-    cs_d = (e_h * mp.PID_CS[2] - csf) * mp.PID_CS[3];
-    cs_pre = fmaf(e_h, mp.PID_CS[0], csi) + cs_d;
-    o.vartheta_zh = satf(cs_pre, PCF(4), PCF(6));
+    e_h = r.href - h_d;  // h_zh - h
+    cs_d = (e_h * c.mp.PID_CS[2] - csf) * c.mp.PID_CS[3];
+    cs_pre = e_h * c.mp.PID_CS[0] + csi + cs_d;
+    vzh_d = fmin(fmax(cs_pre, Pc(4)), Pc(6));
+    o.vartheta_zh = (float)vzh_d;
   } else {
     o.vartheta_zh = 0.f;
   }
   // pitch error in float64
-  double vref_d = (GEN && use_cs >= PCF(146)) ? (double)o.vartheta_zh : r.vartheta;
+  double vref_d = (GEN && use_cs >= PCF(146)) ? vzh_d : r.vartheta;
   double dv_d = vref_d - th_fold;
   o.dv = dv_d;
   float dv = (float)dv_d;
@@ -204,14 +207,14 @@ __device__ __forceinline__ void pass32(const float* __restrict__ sP, const float
   f_h = Vy; f_Vx = ax; f_Vy = ay; f_wz = wzd; f_ssi = ss_i; f_ssf = ss_d;
   f_itse = dv_d * dv_d * t_d;
   if (GEN) {
-    float dzc = cs_pre - satf(cs_pre, PCF(4), PCF(6));
-    float cs_i = e_h * mp.PID_CS[1];
-    o.and_cs = (cs_pre * PCF(292) != dzc) && (sgnf(dzc) == sgnf(cs_i));
+    double dzc = cs_pre - vzh_d;
+    double cs_i = e_h * c.mp.PID_CS[1];
+    o.and_cs = (cs_pre * Pc(292) != dzc) && (((dzc > 0.0) - (dzc < 0.0)) == ((cs_i > 0.0) - (cs_i < 0.0)));
     if (major) memout_cs = (r.flags & FL_MEM_CS) != 0;
-    if (memout_cs) cs_i = PCF(11);
+    if (memout_cs) cs_i = Pc(11);
     f_csi = cs_i; f_csf = cs_d;
   } else {
-    o.and_cs = false; f_csi = 0.f; f_csf = 0.f;
+    o.and_cs = false; f_csi = 0.0; f_csf = 0.0;
   }
 }
 
@@ -226,19 +229,18 @@ __device__ __forceinline__ void model_step32(const float* __restrict__ sP, const
   // float32 copies of the accumulated state for the stage evaluations
   const float y_h = (float)r.h, y_Vx = (float)r.Vx, y_Vy = (float)r.Vy, y_wz = (float)r.wz, y_ssi = (float)r.ssi,
               y_ssf = (float)r.ssf;
-  const float y_csi = GEN ? (float)r.csi : 0.f, y_csf = GEN ? (float)r.csf : 0.f;
-  float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf, X_csi = y_csi, X_csf = y_csf;
-  double X_th = r.th;
-  float a_h = 0, a_Vx = 0, a_Vy = 0, a_wz = 0, a_ssi = 0, a_ssf = 0, a_csi = 0, a_csf = 0, a_th = 0, a_x = 0;
-  double a_dvi = 0, a_itse = 0;
+  float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf;
+  double X_th = r.th, Xd_h = r.h, X_csi = r.csi, X_csf = r.csf;
+  float a_h = 0, a_Vx = 0, a_Vy = 0, a_wz = 0, a_ssi = 0, a_ssf = 0, a_th = 0, a_x = 0;
+  double a_dvi = 0, a_itse = 0, a_csi = 0, a_csf = 0;
   bool memout_ss = false, memout_cs = false;
   float u_n = 0.f;
 #pragma unroll 1
   for (int s = 0; s < 4; s++) {
     const double t_d = s == 0 ? t0 : (s == 3 ? (double)(n + 1) * kH : t0 + 0.5 * kH);
-    float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf;
-    double f_itse;
-    pass32<GEN>(sP, sR, mp, c, s, n, X_th, t_d, X_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, memout_ss,
+    float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf;
+    double f_itse, f_csi, f_csf;
+    pass32<GEN>(sP, sR, mp, c, s, n, X_th, t_d, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, memout_ss,
                 memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
     if (s == 0) {
       // update(): discrete filter, rate-limiter memory, Memory blocks, Derivative history, delay push
@@ -253,7 +255,7 @@ __device__ __forceinline__ void model_step32(const float* __restrict__ sP, const
     const float w = (s == 0 || s == 3) ? 1.f : 2.f;
     a_h = fmaf(w, f_h, a_h); a_Vx = fmaf(w, f_Vx, a_Vx); a_Vy = fmaf(w, f_Vy, a_Vy); a_wz = fmaf(w, f_wz, a_wz);
     a_ssi = fmaf(w, f_ssi, a_ssi); a_ssf = fmaf(w, f_ssf, a_ssf); a_th = fmaf(w, X_wz, a_th);
-    if (GEN) { a_csi = fmaf(w, f_csi, a_csi); a_csf = fmaf(w, f_csf, a_csf); }
+    if (GEN) { a_csi = fma((double)w, f_csi, a_csi); a_csf = fma((double)w, f_csf, a_csf); }
     if (want_x) a_x = fmaf(w, X_Vx, a_x);
     a_dvi = fma((double)w, o.dv, a_dvi);
     a_itse = fma((double)w, f_itse, a_itse);
@@ -267,7 +269,10 @@ __device__ __forceinline__ void model_step32(const float* __restrict__ sP, const
       X_th = fma((double)cf, (double)X_wz, r.th);  // theta' = wz (stage value)
       X_h = fmaf(cf, f_h, y_h); X_Vx = fmaf(cf, f_Vx, y_Vx); X_Vy = fmaf(cf, f_Vy, y_Vy); X_wz = fmaf(cf, f_wz, y_wz);
       X_ssi = fmaf(cf, f_ssi, y_ssi); X_ssf = fmaf(cf, f_ssf, y_ssf);
-      if (GEN) { X_csi = fmaf(cf, f_csi, y_csi); X_csf = fmaf(cf, f_csf, y_csf); }
+      if (GEN) {
+        X_csi = fma((double)cf, f_csi, r.csi); X_csf = fma((double)cf, f_csf, r.csf);
+        Xd_h = fma((double)cf, (double)f_h, r.h);
+      }
     }
   }
   s4.h = X_h; s4.Vx = X_Vx; s4.Vy = X_Vy; s4.wz = X_wz;
@@ -275,7 +280,7 @@ __device__ __forceinline__ void model_step32(const float* __restrict__ sP, const
   const double h6d = kH / 6.0;
   r.h += (double)(h6 * a_h); r.Vx += (double)(h6 * a_Vx); r.Vy += (double)(h6 * a_Vy); r.wz += (double)(h6 * a_wz);
   r.ssi += (double)(h6 * a_ssi); r.ssf += (double)(h6 * a_ssf); r.th += (double)(h6 * a_th);
-  if (GEN) { r.csi += (double)(h6 * a_csi); r.csf += (double)(h6 * a_csf); }
+  if (GEN) { r.csi = fma(h6d, a_csi, r.csi); r.csf = fma(h6d, a_csf, r.csf); }
   if (want_x) r.x += (double)(h6 * a_x);
   r.dvi = fma(h6d, a_dvi, r.dvi);
   r.itse = fma(h6d, a_itse, r.itse);

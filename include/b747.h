@@ -84,6 +84,8 @@ typedef struct b747_episode {
 typedef struct b747_handle b747_handle;
 
 const char *b747_last_error(void);
+/* which: 0 -> ABI version, 1 -> sizeof(b747_cfg), 2 -> sizeof(b747_episode) (binding self-check) */
+int b747_abi_info(int which);
 int b747_obs_dim(int obs_type);
 int64_t b747_done_tick(double tk);
 

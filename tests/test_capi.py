@@ -1,0 +1,102 @@
+"""The C-ABI libraries load and export every symbol the headers declare; without a GPU the entry
+points fail loudly instead of falling back (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libs():
+    from b747_rl_ctrl_b200 import _lib, build
+    build.build_native()
+    return ctypes.CDLL(_lib.LIB_PATH), ctypes.CDLL(_lib.SCALAR_LIB_PATH)
+
+
+def _declared_functions(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b747_[a-z0-9_]+|model_simple_[a-z]+)\s*\(", txt)))
+
+
+def test_batched_abi_symbols(libs):
+    lib, scal = libs
+    names = _declared_functions("b747.h")
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), n
+        assert hasattr(scal, n), n  # model_simple.so is self-contained
+
+
+def test_scalar_abi_symbols(libs):
+    _, scal = libs
+    for n in _declared_functions("b747_scalar.h"):
+        assert hasattr(scal, n), n
+    # the data symbols core/model.py:129-164 binds with in_dll (+ the unbound exports)
+    data = {"state": 6, "sim_time": 1, "vartheta_zh": 1, "U_com_PID": 1, "CXa": 1, "CYa": 1, "mz": 1, "K_alpha": 1,
+            "dCm_ddeltaz": 1, "U_com": 1, "deltaz_RP": 1, "dvartheta": 1, "dvartheta_int": 1, "dvartheta_dt": 1,
+            "dvartheta_dt_dt": 1, "TAE": 1, "ITAE": 1, "TSE": 1, "ITSE": 1, "AE": 1, "IAE": 1, "SE": 1, "ISE": 1,
+            "state0": 6, "h_zh": 1, "use_RP": 1, "use_PID_SS": 1, "use_PID_CS": 1, "PID_SS": 4, "PID_CS": 4,
+            "deltaz": 1, "vartheta": 1, "P": 1, "aero_err": 5, "Iz": 1, "S": 1, "c_": 1, "g": 1, "m0": 1, "use_RL": 1,
+            "alpha": 1, "V": 1, "Mach": 1}
+    for n, k in data.items():
+        v = (ctypes.c_double * k).in_dll(scal, n)
+        assert len(v) == k
+    # .data defaults of the DLL
+    assert list((ctypes.c_double * 6).in_dll(scal, "state0")) == [0, 11000, 259.1667, 0, 0, 0]
+    assert list((ctypes.c_double * 4).in_dll(scal, "PID_SS")) == [-5.9151, -1.2404, -6.6927, 58.0826]
+    assert ctypes.c_double.in_dll(scal, "Iz").value == 67300000.0
+    assert ctypes.c_double.in_dll(scal, "use_RP").value == 1.0
+
+
+def test_struct_layout_matches_ctypes(libs):
+    from b747_rl_ctrl_b200 import _lib
+    lib, _ = libs
+    assert lib.b747_abi_info(0) == _lib.ABI_VERSION
+    assert lib.b747_abi_info(1) == ctypes.sizeof(_lib.Cfg)
+    assert lib.b747_abi_info(2) == ctypes.sizeof(_lib.Episode)
+
+
+def test_field_table(libs):
+    lib, _ = libs
+    lib.b747_field_name.restype = ctypes.c_char_p
+    n = lib.b747_n_fields()
+    names = [lib.b747_field_name(i).decode() for i in range(n)]
+    assert len(set(names)) == n
+    for must in ("h", "q0", "q3", "Vx", "deltaz", "vartheta", "h_zh", "state0_x", "sig_U_com_PID", "sig_ITSE", "tick"):
+        assert must in names
+        assert lib.b747_field_index(must.encode()) == names.index(must)
+    assert lib.b747_field_index(b"nope") == -1
+
+
+def test_no_cpu_fallback(libs):
+    """On a box without a CUDA device creation must fail with B747_ERR_CUDA -- never a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from b747_rl_ctrl_b200 import B747Error, engine
+    with pytest.raises(B747Error, match="no CUDA device"):
+        engine.BatchEngine(n_envs=4)
+    from b747_rl_ctrl_b200.core.model import Model
+    with pytest.raises(B747Error):
+        Model()
+
+
+def test_argument_validation(libs):
+    from b747_rl_ctrl_b200 import _lib, engine
+    lib, _ = libs
+    L = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = engine.make_cfg(n_envs=0)
+    assert L.b747_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_ARG
+    cfg = engine.make_cfg(n_envs=4)
+    cfg.abi_version = 99
+    assert L.b747_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_ARG
+    cfg = engine.make_cfg(n_envs=4, ctrl_type=engine.CTRL_AUTO)  # random reset without an NN in the loop
+    assert L.b747_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_ARG
+    assert b"random reset" in L.b747_last_error()
+    cfg = engine.make_cfg(n_envs=4, dtype=_lib.F32, env_layer=False)
+    assert L.b747_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_ARG
