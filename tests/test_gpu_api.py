@@ -1,0 +1,203 @@
+"""GPU tests of the drop-in surfaces: the scalar model_simple.so boundary bound exactly as
+core/model.py does, Model, Controller/ControllerEnv (gym API) and B747VecEnv (SB3 VecEnv contract)."""
+import ctypes
+import json
+import math
+import os
+import random
+import shutil
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEG = math.pi / 180
+
+
+def _kats():
+    return json.load(open(os.path.join(HERE, "golden", "model_kats.json")))
+
+
+def _tol(name):
+    return {"dvartheta_dt_dt": (1e-6, 1e-9), "dvartheta_dt": (1e-8, 1e-11)}.get(name, (1e-9, 1e-12))
+
+
+def test_scalar_boundary_bound_like_core_model_py():
+    """core/model.py:99-164: copy the library, LoadLibrary, bind 3 functions + globals with in_dll."""
+    from b747_rl_ctrl_b200 import _lib
+    real_T = ctypes.c_double
+    tmp = tempfile.mkdtemp()
+    insts = []
+    for k in range(2):  # two private copies == two independent Model instances
+        path = os.path.join(tmp, f"copy{k}.so")
+        shutil.copyfile(_lib.SCALAR_LIB_PATH, path)
+        insts.append(ctypes.cdll.LoadLibrary(path))
+    dll = insts[0]
+    init, step = getattr(dll, "model_simple_initialize"), getattr(dll, "model_simple_step")
+    state = (real_T * 6).in_dll(dll, "state")
+    sim_time = real_T.in_dll(dll, "sim_time")
+    use_ss = real_T.in_dll(dll, "use_PID_SS")
+    dv = real_T.in_dll(dll, "dvartheta")
+    use_ss.value = 1.0
+    init()
+    assert list(state) == [0.0] * 6 and sim_time.value == 0.0
+    step()
+    k1 = _kats()["K1"]["snaps"]
+    assert sim_time.value == 0.01
+    assert np.allclose(list(state), k1["1"]["state"], rtol=1e-12, atol=1e-13)
+    assert dv.value == pytest.approx(k1["1"]["dvartheta"], rel=1e-12)
+    for _ in range(4):
+        step()
+    assert np.allclose(list(state), k1["5"]["state"], rtol=1e-12, atol=1e-13)
+    # the second copy is untouched (private globals, like one DLL copy per Model)
+    assert real_T.in_dll(insts[1], "sim_time").value == 0.0
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+@pytest.mark.parametrize("name", ["K1", "K3", "K4", "K5"])
+def test_model_dropin_matches_dll_kats(name):
+    """Model attribute surface (core/model.py) stepping on the GPU vs signals recorded from the DLL."""
+    from b747_rl_ctrl_b200.core.model import Model
+    case = _kats()[name]
+    p = case["params"]
+    m = Model(use_PID_SS=bool(p.get("use_PID_SS", 0)), use_PID_CS=bool(p.get("use_PID_CS", 0)),
+              initial_state=np.array(p["state0"]) if "state0" in p else None)
+    assert (m.state == 0).all() and m.time == 0.0 and m.step_num == -1
+    if "h_zh" in p:
+        m.hzh = p["h_zh"]
+    if "aero_err" in p:
+        m.aero_err = np.array(p["aero_err"])
+    m.vartheta_zh = p.get("vartheta", 5 * DEG if name == "K1" else 0.0)
+    if name == "K1":
+        m.vartheta_zh = 0.08726646259971647  # DLL default of `vartheta` (Model.initialize zeroes it)
+    rng = random.Random(0)
+    steps = min(case["steps"], 1300)
+    py2sig = {"time": "sim_time", "vartheta_ref": "vartheta_zh", "deltaz_ref": "U_com_PID", "deltaz_com": "U_com",
+              "deltaz_real": "deltaz_RP", "Kalpha": "K_alpha"}
+    for k in range(steps):
+        if case["elevator"] and k % 5 == 0:
+            m.deltaz = rng.uniform(-0.2967, 0.2967)
+        m.step()
+        snap = case["snaps"].get(str(k + 1))
+        if snap is None:
+            continue
+        assert np.allclose(m.state, snap["state"], rtol=1e-9, atol=1e-12), (name, k + 1)
+        for attr in ["time", "vartheta_ref", "deltaz_ref", "deltaz_com", "deltaz_real", "CXa", "CYa", "mz", "Kalpha",
+                     "dCm_ddeltaz", "dvartheta", "dvartheta_int", "dvartheta_dt", "dvartheta_dt_dt", "TAE", "ITAE",
+                     "TSE", "ITSE", "AE", "IAE", "SE", "ISE"]:
+            sig = py2sig.get(attr, attr)
+            rel, ab = _tol(sig)
+            assert np.allclose(getattr(m, attr), snap[sig], rtol=rel, atol=ab), (name, k + 1, attr)
+    assert m.step_num == steps - 1
+    assert set(m.state_dict) == {"x", "y", "Vx", "Vy", "vartheta", "wz"}
+
+
+def test_controller_env_k7():
+    """SURVEY.md 8c K7 through the ControllerEnv drop-in (gym API), float64."""
+    from b747_rl_ctrl_b200.core.controller import CtrlMode, CtrlType
+    from b747_rl_ctrl_b200.env.ctrl_env import ControllerEnv, ObservationType, RewardType
+    g = np.load(os.path.join(HERE, "golden", "env_golden.npz"))
+    env = ControllerEnv(ObservationType.PID_LIKE, RewardType.CLASSIC, True, True, CtrlType.MANUAL, CtrlMode.DIRECT_CONTROL,
+                        tk=20, reset_ref_mode=None, sample_time=0.05, use_limiter=False, action_max=17 * DEG)
+    assert env.observation_space.shape == (3,) and env.action_space.shape == (1,)
+    env.ctrl.vartheta_func = lambda _: 5 * DEG
+    obs = env.reset(np.array([0, 11000, 250, 0, 0, 0]))
+    assert list(obs) == [0.0, 0.0, 0.0]
+    rng = random.Random(0)
+    ret = 0.0
+    for k in range(400):
+        a = np.array([rng.uniform(-1, 1)])
+        a0 = a[0]
+        obs, r, done, info = env.step(a)
+        assert a[0] == a0 * (17 * DEG)          # the reference scales the caller's array in place
+        assert np.allclose(obs, g["k7/obs"][k], rtol=1e-9, atol=2e-12), k
+        assert abs(r - g["k7/rew"][k]) <= 1e-9
+        assert done == (k == 399) and info == {}
+        ret += r
+    assert ret == pytest.approx(218.4897443782656, abs=1e-8)
+    assert env.ctrl.is_done and env.is_done()
+    assert env.ctrl.model.time == 20.0
+    assert env.ctrl.vartheta_ref == 5 * DEG
+    q = env.ctrl.quality()
+    assert 0 < q < 1
+    # ADD_PROC with a = 0 is the pure PID loop; its return is the published-curve anchor of SURVEY.md 6
+    env = ControllerEnv(ObservationType.PID_LIKE, RewardType.CLASSIC, True, True, CtrlType.MANUAL, CtrlMode.ADD_PROC_CONTROL,
+                        tk=20, reset_ref_mode=None, sample_time=0.05, action_max=1.0)
+    env.ctrl.vartheta_func = lambda _: 5 * DEG
+    env.reset(np.array([0, 11000, 250, 0, 0, 0]))
+    ret = sum(env.step(np.array([0.0]))[1] for _ in range(400))
+    assert ret == pytest.approx(365.092282070656, abs=1e-8)
+
+
+def test_vec_env_contract(oracle):
+    """SB3 VecEnv duck type: shapes, auto-reset observation, terminal_observation, episode info."""
+    from b747_rl_ctrl_b200.vec_env import B747VecEnv
+    from b747_rl_ctrl_b200 import engine as E
+    n = 64
+    venv = B747VecEnv(n, tk=0.5, sample_time=0.05, seed=4, dtype=E.F64)  # 10-step episodes
+    assert venv.num_envs == n and venv.observation_space.shape == (3,) and venv.action_space.shape == (1,)
+    obs = venv.reset()
+    assert obs.shape == (n, 3) and (obs == 0).all()
+    ob = oracle.OracleBatch(oracle.make_cfg(tk=0.5, seed=4), n)
+    ob.reset()
+    rng = np.random.default_rng(1)
+    for k in range(25):
+        a = rng.uniform(-1, 1, (n, 1))
+        venv.step_async(a)
+        obs, rew, dones, infos = venv.step_wait()
+        o_o, r_o, d_o, t_o = ob.step(a[:, 0])
+        assert obs.shape == (n, 3) and rew.shape == (n,) and dones.dtype == bool and len(infos) == n
+        assert np.array_equal(dones, d_o) and np.allclose(obs, o_o, rtol=1e-9, atol=2e-9) and np.allclose(rew, r_o, atol=1e-9)
+        if (k + 1) % 10 == 0:
+            assert dones.all() and (obs == 0).all()
+            for i in range(n):
+                assert np.allclose(infos[i]["terminal_observation"], t_o[i], rtol=1e-9, atol=2e-9)
+                assert infos[i]["episode"]["l"] == 10 and infos[i]["episode"]["r"] > 0
+        else:
+            assert not dones.any() and infos[0] == {}
+    assert venv.env_is_wrapped(None) == [False] * n and venv.seed(1) == [1] * n
+    st = venv.episode_stats()
+    assert st[0] == 2 * n and st[2] == 20 * n
+    venv.close()
+
+
+def test_vec_env_device_tensors():
+    import torch
+    from b747_rl_ctrl_b200.vec_env import B747VecEnv
+    venv = B747VecEnv(4096, device_tensors=True)
+    obs = venv.reset()
+    assert obs.is_cuda and obs.shape == (4096, 3)
+    a = torch.zeros(4096, 1, device="cuda")
+    for _ in range(3):
+        obs, rew, dones, infos = venv.step(a)
+    assert obs.is_cuda and rew.is_cuda and dones.dtype == torch.bool and float(rew.min()) > 0
+    venv.close()
+
+
+def test_reset_mask_and_reset_to():
+    from b747_rl_ctrl_b200 import engine as E
+    import torch
+    n = 256
+    eng = E.BatchEngine(n_envs=n, dtype=E.F64, seed=2)
+    act, obs, rew, done = eng.alloc_io()
+    eng.reset(obs)
+    for _ in range(7):
+        eng.step(act, obs, rew, done)
+    eng.synchronize()
+    assert (eng.get("tick") == 35).all()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::2] = 1
+    h_before = eng.get("h")
+    eng.reset(obs, mask=mask)
+    eng.synchronize()
+    t = eng.get("tick")
+    assert (t[::2] == 0).all() and (t[1::2] == 35).all()
+    assert (eng.get("ep_idx")[::2] == 2).all() and (eng.get("ep_idx")[1::2] == 1).all()
+    assert np.array_equal(eng.get("h")[1::2], h_before[1::2])
+    # explicit episodes (Controller.reset(state0) with a reference)
+    e2 = E.BatchEngine(n_envs=2, dtype=E.F64, reset_ref_mode=E.RESET_NONE)
+    e2.reset_to([E.episode([0, 11000, 250, 0, 0, 0], vref=5 * DEG), E.episode([10, 3000, 150, 5, 0.02, 0.001], vref=-3 * DEG)])
+    assert list(e2.get("h")) == [11000.0, 3000.0] and list(e2.get("vref")) == [5 * DEG, -3 * DEG]
+    assert np.allclose(e2.get("q3"), [0.0, math.sin(0.01)]) and list(e2.get("tick")) == [0, 0]

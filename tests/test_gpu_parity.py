@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical seeded
+inputs, against the committed DLL golden vectors, and -- at BASELINE.json's full size -- through
+size-independent properties.  Bars: float64 mode obs/reward within 1e-9 (relative, with an absolute
+floor for the finite-difference signals), done flags / step counts / episode counts bit-exact;
+f32 mode within the bound stated in DESIGN.md over 1000-step trajectories, done flags bit-exact."""
+import json
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEG = math.pi / 180
+
+
+@pytest.fixture(scope="module")
+def E():
+    import torch
+    assert torch.cuda.is_available()
+    from b747_rl_ctrl_b200 import engine
+    return engine
+
+
+def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=None):
+    """Step engine and oracle in lock-step with the same actions; returns the worst deviations."""
+    cfg_o = O.make_cfg(seed=seed, **kw)
+    eng = E.BatchEngine(n_envs=n, dtype=dtype, seed=seed, auto_reset=True, **kw)
+    ob = O.OracleBatch(cfg_o, n)
+    eng.reset()
+    o0 = ob.reset()
+    assert (o0 == 0).all()
+    rng = np.random.default_rng(seed)
+    amax = 1.0 if cfg_o.norm_act else cfg_o.action_max
+    worst_o = worst_r = 0.0
+    term = np.zeros((n, eng.obs_dim), eng.np_dtype)
+    n_done = 0
+    for k in range(steps):
+        a = rng.uniform(-amax, amax, n).astype(eng.np_dtype)
+        obs, rew, done, term = eng.step_host(a, terminal_obs=term)
+        o_o, r_o, d_o, t_o = ob.step(a.astype(np.float64))
+        assert np.array_equal(done.astype(bool), d_o), f"done flags differ at step {k}"
+        n_done += int(d_o.sum())
+        eo = np.abs(obs.astype(np.float64) - o_o)
+        et = np.abs(term.astype(np.float64) - t_o)
+        er = np.abs(rew.astype(np.float64) - r_o)
+        lim = obs_tol[0] + obs_tol[1] * np.abs(t_o)
+        assert (et <= lim).all(), f"step {k}: terminal/obs deviation {et.max():.3e}"
+        assert (eo <= obs_tol[0] + obs_tol[1] * np.abs(o_o)).all(), f"step {k}: obs deviation {eo.max():.3e}"
+        assert (er <= rew_tol).all(), f"step {k}: reward deviation {er.max():.3e}"
+        worst_o, worst_r = max(worst_o, et.max()), max(worst_r, er.max())
+    st = eng.episode_stats()
+    assert st[0] == n_done
+    return worst_o, worst_r, n_done, eng
+
+
+def test_f64_matches_oracle_config2(E, oracle):
+    """BASELINE configs[1]: 4096 envs, float64, per-step parity (+ 1000-step trajectories on 256 envs)."""
+    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F64, 4096, 120, dict(), 5, (2e-9, 1e-9), 1e-9)
+    print(f"f64 4096x120: max|dobs|={wo:.2e} max|drew|={wr:.2e}")
+    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F64, 256, 1000, dict(), 6, (2e-9, 1e-9), 1e-9)
+    assert nd == 256 * 2  # two auto-resets per env in 1000 steps of 400-step episodes
+    print(f"f64 256x1000: max|dobs|={wo:.2e} max|drew|={wr:.2e}")
+
+
+VARIANTS = {
+    "K10": dict(sample_time=0.10),
+    "K1_tk3": dict(sample_time=None, tk=3.0),
+    "speed_addproc": dict(obs_type=1, ctrl_mode=1, action_max=1.0),
+    "aero_adddirect_osc": dict(obs_type=3, ctrl_mode=3, action_max=10 * DEG, reset_ref_mode=1),
+    "state_angvel_hybrid_dist": dict(obs_type=4, ctrl_mode=2, action_max=2 * DEG, reset_ref_mode=2, disturbance_mode=0),
+    "pidaero_pidlike_limiter": dict(obs_type=2, rew_type=1, use_limiter=True),
+    "quality_semimanual": dict(rew_type=2, ctrl_type=2, reset_ref_mode=2),
+    "minimal": dict(rew_type=3),
+    "tfref_unnormalised": dict(rew_type=4, norm_obs=False, norm_act=False),
+    "fixed_aero_err": dict(disturbance_mode=0, aero_err=[-0.1, 0.1, -0.1, -0.1, 0.1]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_f64_variants_match_oracle(E, oracle, name):
+    kw = VARIANTS[name]
+    steps = 320 if name == "K1_tk3" else 420
+    # un-normalised observations carry raw magnitudes (Vx ~ 250): relative bar only
+    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F64, 96, steps, kw, 9, (2e-9, 1e-9), 1e-9)
+    assert nd >= 96
+    print(f"f64 {name}: max|dobs|={wo:.2e} max|drew|={wr:.2e} episodes={nd}")
+
+
+def test_f64_matches_dll_golden(E):
+    """The kernels against trajectories produced by the reference DLL's own machine code."""
+    g = np.load(os.path.join(HERE, "golden", "env_golden.npz"))
+    meta = json.loads(bytes(g["meta_json"]).decode())
+    for name, m in meta.items():
+        eng = E.BatchEngine(n_envs=m["n"], dtype=E.F64, seed=m["seed"], auto_reset=True, **m["kw"])
+        eng.reset()
+        acts = g[name + "/actions"]
+        term = np.zeros((m["n"], eng.obs_dim))
+        for k in range(m["steps"]):
+            obs, rew, done, term = eng.step_host(acts[:, k], terminal_obs=term)
+            assert np.array_equal(done, g[name + "/done"][:, k]), (name, k)
+            ref = g[name + "/obs"][:, k]
+            assert (np.abs(term - ref) <= 2e-9 + 1e-9 * np.abs(ref)).all(), (name, k, np.abs(term - ref).max())
+            assert np.abs(rew - g[name + "/rew"][:, k]).max() <= 1e-9, (name, k)
+
+
+def test_f32_bound_over_1000_steps(E, oracle):
+    """fp32 mode, canonical config, 1000-step trajectories (2.5 episodes), K = 5 and K = 10.
+    Stated bound: |d obs| <= 1e-5 (normalised units), |d reward| <= 1e-3; done bit-exact."""
+    for K, n in ((5, 512), (10, 256)):
+        wo, wr, nd, _ = _rollout_compare(E, oracle, E.F32, n, 1000, dict(sample_time=K * 0.01), 21, (1e-5, 0.0), 1e-3)
+        assert nd == n * (1000 * K // 2000)
+        print(f"f32 K={K} {n}x1000: max|dobs|={wo:.2e} max|drew|={wr:.2e}")
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_f32_variants_within_bound(E, oracle, name):
+    kw = VARIANTS[name]
+    steps = 320 if name == "K1_tk3" else 420
+    # raw (un-normalised) observations: relative float32 resolution on magnitudes up to ~1e4
+    tol = (1e-5, 2e-6) if not kw.get("norm_obs", True) else (2e-5, 0.0)
+    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F32, 96, steps, kw, 9, tol, 2e-3)
+    print(f"f32 {name}: max|dobs|={wo:.2e} max|drew|={wr:.2e} episodes={nd}")
+
+
+def test_full_size_properties_config3(E, oracle):
+    """BASELINE configs[2]: 1M envs, f32, K=10, in-kernel auto-reset -- size-independent properties."""
+    import torch
+    n, K = 1 << 20, 10
+    kw = dict(sample_time=K * 0.01)
+    eng = E.BatchEngine(n_envs=n, dtype=E.F32, seed=1, **kw)
+    act, obs, rew, done = eng.alloc_io()
+    eng.reset(obs)
+    eng.synchronize()
+    assert float(obs.abs().max()) == 0.0
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    # sharding invariance: a 4096-env handle holding the same GLOBAL env ids gives bit-identical results
+    lo = 777 * 128
+    sl = E.BatchEngine(n_envs=4096, dtype=E.F32, seed=1, env_id_offset=lo, **kw)
+    a2, o2, r2, d2 = sl.alloc_io()
+    sl.reset(o2)
+    # oracle on 512 of those envs
+    ob = oracle.OracleBatch(oracle.make_cfg(seed=1, **kw), 512, env_id_offset=lo)
+    ob.reset()
+    total_done = 0
+    ret_first_episode = 0.0
+    for k in range(205):
+        act.uniform_(-1, 1, generator=gen)
+        eng.step(act, obs, rew, done)
+        a2.copy_(act[lo:lo + 4096])
+        sl.step(a2, o2, r2, d2)
+        eng.synchronize(); sl.synchronize()
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert float(rew.min()) >= -0.2 and float(rew.max()) <= 1.0 + 1e-6   # CLASSIC reward range
+        assert torch.equal(obs[lo:lo + 4096], o2) and torch.equal(rew[lo:lo + 4096], r2)
+        assert torch.equal(done[lo:lo + 4096], d2)
+        nd = int(done.sum())
+        # tk = 20 s at K = 10: every env finishes exactly at env step 200 (done <=> tick >= 2000), none before
+        assert nd == (n if k == 199 else 0)
+        total_done += nd
+        if k < 200:
+            ret_first_episode += float(rew.double().sum())
+        o_o, r_o, d_o, _ = ob.step(act[lo:lo + 512].double().cpu().numpy())
+        assert np.array_equal(d_o, done[lo:lo + 512].cpu().numpy().astype(bool))
+        assert np.abs(obs[lo:lo + 512].double().cpu().numpy() - o_o).max() <= 1e-5
+        assert np.abs(rew[lo:lo + 512].double().cpu().numpy() - r_o).max() <= 1e-3
+        if k == 199:
+            assert float(obs.abs().max()) == 0.0   # auto-reset returns the (all-zero) reset observation
+    assert total_done == n
+    # checksum of checksums: the in-kernel episode statistics equal the sums of the per-step outputs
+    st = eng.episode_stats()
+    assert st[0] == n and st[2] == 200.0 * n
+    assert abs(st[1] - ret_first_episode) <= 1e-9 * abs(ret_first_episode)
+    ret, ln = eng.last_episode()
+    assert (ln == 200).all() and abs(ret.sum() - st[1]) <= 1e-9 * abs(st[1])
+    # determinism: two fresh handles with the same seed replay the same step bit for bit
+    outs = []
+    for _ in range(2):
+        e2 = E.BatchEngine(n_envs=n, dtype=E.F32, seed=1, **kw)
+        b_act, b_obs, b_rew, b_done = e2.alloc_io()
+        e2.reset(b_obs)
+        b_act.uniform_(-1, 1, generator=torch.Generator(device="cuda").manual_seed(0))
+        e2.step(b_act, b_obs, b_rew, b_done)
+        e2.synchronize()
+        outs.append((b_obs.clone(), b_rew.clone()))
+        e2.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
