@@ -60,8 +60,40 @@ def bench(dtype, n, K, iters=20):
     print(f"bench dtype={'f64' if dtype == E.F64 else 'f32'} n={n} K={K}: {dt*1e3:.3f} ms/step -> {n/dt:.3e} env-steps/s")
 
 
+def variants():
+    """Worst f32-vs-oracle deviations per configuration family (to set the stated bounds)."""
+    sys.path.insert(0, "tests")
+    from tests.test_gpu_parity import VARIANTS
+    for name, kw in sorted(VARIANTS.items()):
+        steps = 320 if name == "K1_tk3" else 420
+        n = 96
+        cfg_o = O.make_cfg(seed=9, **kw)
+        eng = E.BatchEngine(n_envs=n, dtype=E.F32, seed=9, auto_reset=True, **kw)
+        ob = O.OracleBatch(cfg_o, n)
+        eng.reset(); ob.reset()
+        rng = np.random.default_rng(9)
+        amax = 1.0 if cfg_o.norm_act else cfg_o.action_max
+        term = np.zeros((n, eng.obs_dim), np.float32)
+        wo = np.zeros(eng.obs_dim); wrel = np.zeros(eng.obs_dim); wr = 0.0; bad = 0
+        for k in range(steps):
+            a = rng.uniform(-amax, amax, n).astype(np.float32)
+            obs, rew, done, term = eng.step_host(a, terminal_obs=term)
+            o_o, r_o, d_o, t_o = ob.step(a.astype(np.float64))
+            bad += int((done.astype(bool) != d_o).sum())
+            e = np.abs(term.astype(np.float64) - t_o)
+            wo = np.maximum(wo, e.max(axis=0))
+            wrel = np.maximum(wrel, (e / np.maximum(np.abs(t_o), 1e-2)).max(axis=0))
+            wr = max(wr, np.abs(rew - r_o).max())
+        print(f"{name:28s} done-mismatch {bad} |drew| {wr:.2e} |dobs| {np.array2string(wo, precision=1)} rel(floor 1e-2) {np.array2string(wrel, precision=1)}", flush=True)
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variants()
+        run(E.F32, 512, 1000, 5)
+        run(E.F32, 256, 1000, 10)
+        sys.exit(0)
     run(E.F64, 256, 420, 5)
     run(E.F32, 256, 420, 5)
     run(E.F64, 64, 60, 5, obs_type=O.OBS_PID_SPEED_AERO, reset_ref_mode=O.RESET_OSCILLATING)
