@@ -8,7 +8,7 @@ import math
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb747_b200.so")
+LIB_PATH = os.environ.get("B747_LIB_PATH") or os.path.join(HERE, "lib", "libb747_b200.so")
 SCALAR_LIB_PATH = os.path.join(HERE, "lib", "model_simple.so")
 
 ABI_VERSION = 1

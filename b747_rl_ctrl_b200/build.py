@@ -21,11 +21,12 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 # the reference DLL is SSE2 code that rounds every product and sum separately.
 UNITS = {
     "b747_kernels_f64.cu": ["-fmad=false"],
-    "b747_kernels_f32.cu": [],
+    # throughput kernels: approximate (1-2 ulp) float32 division / sqrt; float64 ops unaffected
+    "b747_kernels_f32.cu": ["-prec-div=false", "-prec-sqrt=false"],
     "b747_capi.cu": [],
     "b747_scalar.cu": [],
 }
-HEADERS = ["b747_common.cuh", "b747_kernels.h", "b747_model_f64.cuh", "b747_model_mx.cuh",
+HEADERS = ["b747_common.cuh", "b747_kernels.h", "b747_model_f64.cuh", "b747_model_mx.cuh", "b747_poly.h",
            "../../include/b747.h", "../../include/b747_params.h", "../../include/b747_scalar.h"]
 
 

@@ -59,6 +59,8 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
     r.tf_tp = 0.f; r.sig_vzh = 0.f;
   }
   r.vartheta = 0.0;
+#pragma unroll
+  for (int k = 0; k < N_AXES; k++) r.ax[k] = 0;  // interval cache: re-searched on first use
 }
 
 // `full`: also the groups a step never changes (reference, aero sums, state0) -- reset paths only.
@@ -138,24 +140,26 @@ __device__ __forceinline__ float nan_to_num_f(float x) {
   return x;
 }
 
-__device__ __forceinline__ void load_tables32(float* sP, float* sR) {
-  static const __device__ double gP[kNP] = B747_P_INIT;
-  for (int k = threadIdx.x; k < kNP; k += blockDim.x) {
-    sP[k] = (float)gP[k];
-    sR[k] = (k + 1 < kNP) ? (float)(1.0 / (gP[k + 1] - gP[k])) : 0.f;
-  }
+// look-up tables in the fast path's layout, built at compile time (b747_model_mx.cuh)
+__device__ const FastTables gFastTables = make_fast_tables();
+
+__device__ __forceinline__ void load_tables32(float4* sT) {
+  const float4* g = reinterpret_cast<const float4*>(gFastTables.v);
+  for (int k = threadIdx.x; k < kFastCells; k += blockDim.x) sT[k] = g[k];
   __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
+#ifndef B747_F32_MINBLOCKS
+#define B747_F32_MINBLOCKS 4
+#endif
 template <bool GEN>
-__global__ void __launch_bounds__(128) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
+__global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                     uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
-  __shared__ float sP[kNP];
-  __shared__ float sR[kNP];
+  __shared__ float4 sT[kFastCells];
   __shared__ EpStatsSmem sst;
-  load_tables32(sP, sR);
+  load_tables32(sT);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < c.n_envs;
   const size_t np = (size_t)c.n_pad;
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(128) k_env_step32(DevCfg c, MP32 mp, StateF32 
     Stage4Mx s4;
     const bool want_x = GEN && c.obs_type == B747_OBS_MODEL_STATE;
 #pragma unroll 1
-    for (int k = 0; k < c.substeps; k++) model_step32<GEN>(sP, sR, mp, c, r, o, s4, want_x);
+    for (int k = 0; k < c.substeps; k++) model_step32<GEN>(sT, mp, c, r, o, s4, want_x);
     r.sig_upid = o.U_com_PID; r.sig_vzh = o.vartheta_zh;
     // stage-4 Derivative-block signals (float64 differences of the pitch error)
     const double dv_dt = (o.dv - r.d1_u) * 100.0;
@@ -369,7 +373,7 @@ bool f32_is_lean(const DevCfg& c) {
 
 static MP32 make_mp32(const ModelParams& m) {
   MP32 p;
-  for (int k = 0; k < 4; k++) { p.PID_SS[k] = (float)m.PID_SS[k]; p.PID_CS[k] = (float)m.PID_CS[k]; }
+  for (int k = 0; k < 4; k++) p.PID_SS[k] = (float)m.PID_SS[k];
   p.P = (float)m.P; p.g = (float)m.g; p.inv_m0 = (float)(1.0 / m.m0);
   p.half_S = (float)(Pc(134) * m.S);
   p.half_Sc_over_Iz = (float)(Pc(135) * m.S * m.c_ / m.Iz);

@@ -2,21 +2,27 @@
 // K fused RK4 substeps per launch with the state held in registers.
 //
 // Same block diagram as b747_model_f64.cuh (model_simple_step dll@0x16d0),
-// re-formulated for the FP32/XU pipes of an SM:
+// re-formulated for the FP32 issue rate of an SM (ncu r1a: the kernel is instruction-issue bound,
+// 561 warp instructions per diagram pass, half of them compare/select/move work of the table
+// searches and libm calls):
 //  * aerodynamics, atmosphere, trigonometry, table look-ups, actuator and PIDs in float32;
 //  * the attitude is carried as the pitch angle itself (theta' = wz) instead of the quaternion the
 //    DLL integrates and re-normalises: for a pitch-only rotation the two are the same ODE
 //    (q = (cos th/2, 0, 0, sin th/2)), and RK4 on either differs by O((wz h)^5) ~ 1e-20;
-//    sin/cos of the body rotation then need no asin;
 //  * the pitch-error chain -- theta, dvartheta = ref - theta, its integral, ITSE and the two
-//    finite-difference Derivative blocks -- is kept in float64, because the observation and the
-//    CLASSIC reward difference it over 5..10 ms (hard part 3); B200 issues DFMA at half
-//    the FFMA rate, so these ~10 operations per pass are nearly free;
+//    finite-difference Derivative blocks -- is kept in float64 (the observation and the CLASSIC reward
+//    difference it over 5..10 ms, SURVEY.md 7 hard part 3); B200 issues DFMA at half the FFMA rate,
+//    so these ~10 operations per pass are nearly free;
 //  * every integrator state is accumulated in float64 across steps (y += h/6 * sum), the stage
 //    values inside a step are float32;
-//  * sin(alpha), cos(alpha) come from the body-axis velocity components (-wb/V, ub/V);
-//    density uses exp2/log2; table fractions use precomputed reciprocal breakpoint spacings;
-//    breakpoint searches are branch-free compare chains against immediates;
+//  * look-ups: per axis ONE 128-bit shared-memory load returns {valid-lo, valid-hi, breakpoint,
+//    1/spacing} of the cached interval; the cached interval index is validated with two compares
+//    and only re-searched (incrementally) when the operand left the interval -- Mach, alpha and h
+//    move by ~1e-4 of an interval per pass.  Each 2-D table cell is one 128-bit load of
+//    {t00, t10-t00, t01, t11-t01};
+//  * sin/cos(theta), atan(wb/ub) and the ISA density power are short float32 polynomials
+//    (b747_poly.h, generated + validated by tools/gen_poly.py) with libm fall-backs outside their
+//    fitted ranges; sin(alpha), cos(alpha) come from the body-axis velocity components;
 //  * the transport delay (0.03 s = 3 steps), the Derivative and rate-limiter stamps are resolved
 //    from the integer tick, so no time-stamp arithmetic is left in floating point;
 //  * states that no observation/reward reads (ITAE, IAE, ISE; x and the altitude-loop PID unless the
@@ -25,6 +31,11 @@
 #include <math.h>
 
 #include "b747_common.cuh"
+#include "b747_poly.h"
+
+#ifndef B747_UNROLL_STAGES
+#define B747_UNROLL_STAGES 1  // 1: the four diagram passes of a model step are specialised copies; 0: one rolled loop
+#endif
 
 namespace b747 {
 
@@ -36,9 +47,80 @@ template <int I>
 struct PF { static constexpr float v = (float)Pc(I); };
 #define PCF(i) (PF<(i)>::v)
 
+// the ISA temperature ratio is clamped by the troposphere limits, so the density polynomial's
+// fitted range always covers it
+static_assert((Pc(16) - Pc(17) * Pc(19)) * Pc(127) > 0.70 && (Pc(16) - Pc(18) * Pc(19)) * Pc(127) < 1.01,
+              "ISA temperature ratio leaves the range of the density polynomial (tools/gen_poly.py)");
+static_assert(Pc(42) == Pc(276) && Pc(43) == Pc(277) && Pc(44) == Pc(278) && Pc(45) == Pc(279),
+              "CYa and mz are expected to share their Mach breakpoints");
+
+// ---------------------------------------------------------------------------------------------
+// Look-up tables in the layout the fast path reads (built at compile time from model_simple_P).
+// Axis a, interval i (0..M-1):  {lo, hi, bp[i], 1/(bp[i+1]-bp[i])}; lo of the first and hi of the last
+// interval are NaN, so that `u < lo || u >= hi` is false there (end intervals extrapolate, like
+// look2_binlx) and false for a NaN operand (the search then keeps its interval instead of running away).
+// ---------------------------------------------------------------------------------------------
+enum { AX_Ma = 0, AX_Aa, AX_Mb, AX_C, AX_H, AX_Mc, AX_Ac, AX_Ab, N_AXES };
+struct AxisDef { int base, M; };
+__host__ __device__ constexpr AxisDef axis_def(int a) {
+  constexpr AxisDef d[N_AXES] = {{42, 3}, {46, 4}, {108, 3}, {112, 13}, {201, 4}, {206, 9}, {225, 6}, {280, 10}};
+  return d[a];
+}
+__host__ __device__ constexpr int axis_off(int a) {  // float4 index of axis a's first interval
+  int o = 0;
+  for (int k = 0; k < a; k++) o += axis_def(k).M;
+  return o;
+}
+constexpr int kAxisCells = axis_off(N_AXES);  // 52
+enum { TB_CYa = 0, TB_CXa, TB_dCm, TB_mz, N_TABS };
+struct TabDef { int base, ax0, ax1, stride; };
+__host__ __device__ constexpr TabDef tab_def(int t) {
+  constexpr TabDef d[N_TABS] = {{22, AX_Ma, AX_Aa, 4}, {52, AX_Mb, AX_C, 4}, {151, AX_H, AX_Mc, 5}, {232, AX_Ma, AX_Ab, 4}};
+  return d[t];
+}
+__host__ __device__ constexpr int tab_off(int t) {  // float4 index of table t's first cell
+  int o = kAxisCells;
+  for (int k = 0; k < t; k++) o += axis_def(tab_def(k).ax0).M * axis_def(tab_def(k).ax1).M;
+  return o;
+}
+constexpr int kKaOff = tab_off(N_TABS);                 // K_alpha: {t[i], t[i+1]-t[i], -, -} per interval
+constexpr int kFastCells = kKaOff + axis_def(AX_Ac).M;  // float4 count
+
+struct FastTables { float v[kFastCells * 4]; };
+constexpr FastTables make_fast_tables() {
+  FastTables T{};
+  const float qnan = __builtin_nanf("");
+  for (int a = 0; a < N_AXES; a++) {
+    const AxisDef d = axis_def(a);
+    for (int i = 0; i < d.M; i++) {
+      float* q = T.v + (axis_off(a) + i) * 4;
+      q[0] = i == 0 ? qnan : (float)Pc(d.base + i);
+      q[1] = i == d.M - 1 ? qnan : (float)Pc(d.base + i + 1);
+      q[2] = (float)Pc(d.base + i);
+      q[3] = (float)(1.0 / (Pc(d.base + i + 1) - Pc(d.base + i)));
+    }
+  }
+  for (int t = 0; t < N_TABS; t++) {
+    const TabDef d = tab_def(t);
+    const int M0 = axis_def(d.ax0).M, M1 = axis_def(d.ax1).M;
+    for (int i1 = 0; i1 < M1; i1++)
+      for (int i0 = 0; i0 < M0; i0++) {
+        float* q = T.v + (tab_off(t) + i1 * M0 + i0) * 4;
+        const int o = d.base + i1 * d.stride + i0;
+        q[0] = (float)Pc(o); q[1] = (float)(Pc(o + 1) - Pc(o));
+        q[2] = (float)Pc(o + d.stride); q[3] = (float)(Pc(o + d.stride + 1) - Pc(o + d.stride));
+      }
+  }
+  for (int i = 0; i < axis_def(AX_Ac).M; i++) {
+    float* q = T.v + (kKaOff + i) * 4;
+    q[0] = (float)Pc(218 + i); q[1] = (float)(Pc(218 + i + 1) - Pc(218 + i)); q[2] = 0.f; q[3] = 0.f;
+  }
+  return T;
+}
+
 // float copies of the uniform tunables + folded constants (built on the host, b747_kernels_f32.cu)
 struct MP32 {
-  float PID_SS[4], PID_CS[4];
+  float PID_SS[4];
   float P, g, inv_m0, half_S, half_Sc_over_Iz, use_RP, use_RL, use_PID_SS;
 };
 
@@ -53,10 +135,12 @@ struct RegsMx {
   double oscA[3], oscf[3];
   int tick, flags;
   uint32_t ep_idx;
+  int ax[N_AXES];                                  // cached interval of every look-up axis, as a byte offset (16*i)
 };
 
 struct PassMx {
-  double dv, dv_dt;
+  double dv;
+  float dvf;
   float th, V, alpha, Mach, CXa, CYa, mz, K_alpha, dCm, U_com, U_com_PID, deltaz_RP, vartheta_zh, td, rl_out;
   bool and_ss, and_cs;
 };
@@ -65,93 +149,165 @@ struct PassMx {
 struct Stage4Mx { float h, Vx, Vy, wz, x; double dvi, itse; };
 
 __device__ __forceinline__ float satf(float u, float lo, float hi) { return fminf(fmaxf(u, lo), hi); }
+// single-instruction MUFU forms (operands here are far from the denormal range)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ int sgnf(float x) { return (x > 0.f) - (x < 0.f); }
 
-// index of the breakpoint interval containing u (look2_binlx prelookup semantics: clamp to the end
-// intervals, which extrapolate) + fraction; breakpoints are immediates, spacing reciprocals in smem.
-template <int B, int M>
-__device__ __forceinline__ int prelook32(float u, const float* __restrict__ sP, const float* __restrict__ sR, float& frac) {
-  int idx = 0;
-#pragma unroll
-  for (int j = 1; j < M; j++) idx += (u >= (float)Pc(B + j)) ? 1 : 0;
-  frac = (u - sP[B + idx]) * sR[B + idx];
-  return idx;
+// ---- rare paths, kept out of line so that the pass loop stays small in the instruction cache ----
+__device__ __noinline__ float atan2_far(float y, float x) { return atan2f(y, x); }
+
+// alpha = -atan2(wb, ub)
+__device__ __forceinline__ float alpha_of(float wb, float ub) {
+  const float q = wb * rcp_fast(ub);
+  if (ub > 0.f && fabsf(q) <= poly::ATAN_MAX) {
+    const float z = q * q;
+    float p = fmaf(poly::ATAN6, z, poly::ATAN5); p = fmaf(p, z, poly::ATAN4); p = fmaf(p, z, poly::ATAN3);
+    p = fmaf(p, z, poly::ATAN2); p = fmaf(p, z, poly::ATAN1); p = fmaf(p, z, poly::ATAN0);
+    return -fmaf(q * z, p, q);
+  }
+  return -atan2_far(wb, ub);
 }
 
-__device__ __forceinline__ float bilin32(const float* __restrict__ tab, int i0, float f0, int i1, float f1, int stride) {
-  const float* p = tab + i1 * stride + i0;
-  float a = p[0], b = p[1], c = p[stride], d = p[stride + 1];
-  float yL = fmaf(b - a, f0, a);
-  float yR = fmaf(d - c, f0, c);
+// One axis: validate the cached interval (two compares), re-search incrementally if the operand left
+// it, return the interval record.  `off` is the byte offset 16*interval.
+template <int A>
+__device__ __forceinline__ float4 axis_lookup(const float4* __restrict__ sT, float u, int& off) {
+  const char* base = (const char*)(sT + axis_off(A));
+  float4 q = *(const float4*)(base + off);
+  while ((u < q.x) || (u >= q.y)) {  // NaN end markers / NaN operand terminate the search
+    off += (u >= q.y) ? 16 : -16;
+    q = *(const float4*)(base + off);
+  }
+  return q;
+}
+
+template <int A>
+__device__ __forceinline__ float4 axis_peek(const float4* __restrict__ sT, int off) {
+  return *(const float4*)((const char*)(sT + axis_off(A)) + off);
+}
+__device__ __forceinline__ bool axis_miss(float u, const float4& q) { return (u < q.x) | (u >= q.y); }
+
+template <int T>
+__device__ __forceinline__ float table2(const float4* __restrict__ sT, int off0, float f0, int off1, float f1) {
+  constexpr int M0 = axis_def(tab_def(T).ax0).M;
+  const float4 c = *(const float4*)((const char*)(sT + tab_off(T)) + off1 * M0 + off0);
+  const float yL = fmaf(c.y, f0, c.x);
+  const float yR = fmaf(c.w, f0, c.z);
   return fmaf(yR - yL, f1, yL);
 }
 
-// One pass over the diagram at a stage state.  dt_last = t - (stamp of the last update) as an exact
-// constant (0.01 or 0.005), stage: 0 major, 1/2 half steps, 3 full step.
+// One pass over the diagram at a stage state.  stage: 0 major, 1/2 half steps, 3 full step.
 template <bool GEN>
-__device__ __forceinline__ void pass32(const float* __restrict__ sP, const float* __restrict__ sR, const MP32& mp,
-                                       const DevCfg& c, int stage, int n, double th_d, double t_d, float h, double h_d,
-                                       float Vx, float Vy, float wz, float ssi, float ssf, double csi, double csf,
-                                       RegsMx& r, bool& memout_ss, bool& memout_cs, PassMx& o, float& f_h, float& f_Vx,
-                                       float& f_Vy, float& f_wz, float& f_ssi, float& f_ssf, double& f_csi,
-                                       double& f_csf, double& f_itse) {
+__device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, int stage, int n,
+                                       double th_d, float t_f, float h, double h_d, float Vx, float Vy, float wz,
+                                       float ssi, float ssf, double csi, double csf, RegsMx& r, bool& memout_ss,
+                                       bool& memout_cs, PassMx& o, float& f_h, float& f_Vx, float& f_Vy, float& f_wz,
+                                       float& f_ssi, float& f_ssf, double& f_csi, double& f_csf, float& f_itse) {
   const bool major = stage == 0;
-  // attitude: the DLL's th = asin(sin(theta)) folds beyond +-90 deg; keep that (rare) behaviour
-  float thf = (float)th_d;
+  // attitude: polynomial sin/cos for |theta| <= pi/2; beyond that (libm sincos and the DLL's
+  // principal-value fold asin(sin(theta))) sits behind one rare branch
+  float thf = __double2float_rn(th_d);
   float sn, cs;
-  sincosf(thf, &sn, &cs);
   double th_fold = th_d;
-  if (fabsf(thf) > 1.57079632679f) {  // rare: keep the DLL's principal-value pitch
-    th_fold = asin(sin(th_d));
-    thf = (float)th_fold;
-    cs = fabsf(cs);
+  static_assert(poly::SINCOS_MAX >= 1.57079632679f, "sin/cos polynomial must cover the unfolded pitch range");
+  if (fabsf(thf) > 1.57079632679f) {
+    // rare: beyond +-90 deg the DLL's pitch asin(sin(theta)) folds back.  With k = round(theta/pi) and
+    // r = theta - k*pi (two-constant Cody-Waite reduction in float64): asin(sin(theta)) = (-1)^k r, and the
+    // DLL's sin/cos of that folded pitch are sin(theta) and |cos(theta)| = cos(r).
+    const double k = rint(th_d * 0.318309886183790671538);
+    double rr = fma(-k, 3.141592653589793116, th_d);
+    rr = fma(-k, 1.2246467991473532e-16, rr);
+    th_fold = (((int)k) & 1) ? -rr : rr;
+    thf = __double2float_rn(th_fold);
+  }
+  {
+    const float z = thf * thf;
+    float ps = fmaf(poly::SIN4, z, poly::SIN3); ps = fmaf(ps, z, poly::SIN2); ps = fmaf(ps, z, poly::SIN1); ps = fmaf(ps, z, poly::SIN0);
+    float pc = fmaf(poly::COS4, z, poly::COS3); pc = fmaf(pc, z, poly::COS2); pc = fmaf(pc, z, poly::COS1); pc = fmaf(pc, z, poly::COS0);
+    sn = fmaf(thf * z, ps, thf);
+    cs = fmaf(z, pc, 1.0f);
   }
   o.th = thf;
-  float ub = fmaf(cs, Vx, sn * Vy);
-  float wb = fmaf(cs, Vy, -sn * Vx);
-  float V2 = fmaf(ub, ub, wb * wb);
-  float rV = rsqrtf(V2);
-  float V = V2 * rV;
-  float alpha = -atan2f(wb, ub);
-  float sa = -wb * rV, ca = ub * rV;
+  const float ub = fmaf(cs, Vx, sn * Vy);
+  const float wb = fmaf(cs, Vy, -sn * Vx);
+  const float V2 = fmaf(ub, ub, wb * wb);
+  const float rV = rsqrt_fast(V2);
+  const float V = V2 * rV;
+  const float alpha = alpha_of(wb, ub);
+  const float sa = -wb * rV, ca = ub * rV;
   o.V = V; o.alpha = alpha;
   // ISA atmosphere
-  float hs = fminf(fmaxf(h, PCF(18)), PCF(17));
-  float T = fmaf(-hs, PCF(19), PCF(16));
-  float Mach = V * rsqrtf(T * PCF(20));
-  float ad = alpha * PCF(21);
+  const float hs = fminf(fmaxf(h, PCF(18)), PCF(17));
+  const float T = fmaf(-hs, PCF(19), PCF(16));
+  const float Mach = V * rsqrt_fast(T * PCF(20));
+  const float ad = alpha * PCF(21);
   o.Mach = Mach;
-  // look-ups (Mach axis of CYa and mz share breakpoints P[42..45] == P[276..279])
-  float fMa, fMb, fMc, fAa, fAb, fAc, fH, fC;
-  int iMa = prelook32<42, 3>(Mach, sP, sR, fMa);
-  int iAa = prelook32<46, 4>(ad, sP, sR, fAa);
-  float CYa = bilin32(sP + 22, iMa, fMa, iAa, fAa, 4) * r.sumA[1];
-  int iMb = prelook32<108, 3>(Mach, sP, sR, fMb);
-  int iC = prelook32<112, 13>(CYa, sP, sR, fC);
-  float CXa = bilin32(sP + 52, iMb, fMb, iC, fC, 4) * r.sumA[0];
-  o.CYa = CYa; o.CXa = CXa;
-  int iH = prelook32<201, 4>(h, sP, sR, fH);
-  int iMc = prelook32<206, 9>(Mach, sP, sR, fMc);
-  float dCm = bilin32(sP + 151, iH, fH, iMc, fMc, 5) * r.sumA[3];
-  int iAc = prelook32<225, 6>(ad, sP, sR, fAc);
-  float Ka = fmaf(sP[218 + iAc + 1] - sP[218 + iAc], fAc, sP[218 + iAc]) * r.sumA[4];
-  int iAb = prelook32<280, 10>(ad, sP, sR, fAb);
-  float mz = bilin32(sP + 232, iMa, fMa, iAb, fAb, 4) * r.sumA[2];
-  o.dCm = dCm; o.K_alpha = Ka; o.mz = mz;
-  // density: rho0 * (T/T0)^(g/(LR)-1) * exp(g/R * sat(11000-h) / T)
-  float Tr = T * PCF(127);
-  float rho = PCF(129) * exp2f((PCF(128) - 1.0f) * log2f(Tr));
-  float dh = PCF(130) - h;
-  if (dh < PCF(131)) {  // above the tropopause (rare for this envelope)
-    float xs = fmaxf(dh, PCF(132));
-    rho *= __expf(xs * PCF(133) / T);
+  // look-ups.  Fast path: load the cached interval record of every axis whose operand is already known
+  // (7 x LDS.128), validate all of them with one combined predicate and branch once; the re-search of an
+  // axis that left its interval is rare (Mach, alpha, h move ~1e-4 of an interval per pass).
+  float fMa, fAa, fMb, fH, fMc, fAc, fAb;
+  bool miss;
+  {
+    float4 q;
+    q = axis_peek<AX_Ma>(sT, r.ax[AX_Ma]); miss = axis_miss(Mach, q); fMa = (Mach - q.z) * q.w;
+    q = axis_peek<AX_Aa>(sT, r.ax[AX_Aa]); miss |= axis_miss(ad, q); fAa = (ad - q.z) * q.w;
+    q = axis_peek<AX_Mb>(sT, r.ax[AX_Mb]); miss |= axis_miss(Mach, q); fMb = (Mach - q.z) * q.w;
+    q = axis_peek<AX_H>(sT, r.ax[AX_H]); miss |= axis_miss(h, q); fH = (h - q.z) * q.w;
+    q = axis_peek<AX_Mc>(sT, r.ax[AX_Mc]); miss |= axis_miss(Mach, q); fMc = (Mach - q.z) * q.w;
+    q = axis_peek<AX_Ac>(sT, r.ax[AX_Ac]); miss |= axis_miss(ad, q); fAc = (ad - q.z) * q.w;
+    q = axis_peek<AX_Ab>(sT, r.ax[AX_Ab]); miss |= axis_miss(ad, q); fAb = (ad - q.z) * q.w;
+    if (miss) {  // rare: some operand left its cached interval -> incremental re-search
+      q = axis_lookup<AX_Ma>(sT, Mach, r.ax[AX_Ma]); fMa = (Mach - q.z) * q.w;
+      q = axis_lookup<AX_Aa>(sT, ad, r.ax[AX_Aa]); fAa = (ad - q.z) * q.w;
+      q = axis_lookup<AX_Mb>(sT, Mach, r.ax[AX_Mb]); fMb = (Mach - q.z) * q.w;
+      q = axis_lookup<AX_H>(sT, h, r.ax[AX_H]); fH = (h - q.z) * q.w;
+      q = axis_lookup<AX_Mc>(sT, Mach, r.ax[AX_Mc]); fMc = (Mach - q.z) * q.w;
+      q = axis_lookup<AX_Ac>(sT, ad, r.ax[AX_Ac]); fAc = (ad - q.z) * q.w;
+      q = axis_lookup<AX_Ab>(sT, ad, r.ax[AX_Ab]); fAb = (ad - q.z) * q.w;
+    }
   }
-  float rV2 = rho * V2;
-  float qS = rV2 * mp.half_S;
-  float mD = PCF(126) * CXa * qS;
-  float Lf = qS * CYa;
-  float Fx = fmaf(mD, ca, fmaf(sa, Lf, mp.P));
-  float Fy = fmaf(ca, Lf, -mD * sa);
+  float CYa = table2<TB_CYa>(sT, r.ax[AX_Ma], fMa, r.ax[AX_Aa], fAa);
+  if (GEN) CYa *= r.sumA[1];
+  const float4 qC = axis_lookup<AX_C>(sT, CYa, r.ax[AX_C]);
+  float CXa = table2<TB_CXa>(sT, r.ax[AX_Mb], fMb, r.ax[AX_C], (CYa - qC.z) * qC.w);
+  if (GEN) CXa *= r.sumA[0];
+  o.CYa = CYa; o.CXa = CXa;
+  float dCm = table2<TB_dCm>(sT, r.ax[AX_H], fH, r.ax[AX_Mc], fMc);
+  const float4 kc = *(const float4*)((const char*)(sT + kKaOff) + r.ax[AX_Ac]);
+  float Ka = fmaf(kc.y, fAc, kc.x);
+  float mz = table2<TB_mz>(sT, r.ax[AX_Ma], fMa, r.ax[AX_Ab], fAb);
+  if (GEN) { dCm *= r.sumA[3]; Ka *= r.sumA[4]; mz *= r.sumA[2]; }
+  o.dCm = dCm; o.K_alpha = Ka; o.mz = mz;
+  // density: rho0 * (T/T0)^(g/(LR)-1) [* exp(g/R * sat(11000-h) / T) above the tropopause]
+  const float u = fmaf(T, PCF(127), -poly::RHO_CENTER);
+  float pr = fmaf(poly::RHO6, u, poly::RHO5); pr = fmaf(pr, u, poly::RHO4); pr = fmaf(pr, u, poly::RHO3);
+  pr = fmaf(pr, u, poly::RHO2); pr = fmaf(pr, u, poly::RHO1); pr = fmaf(pr, u, poly::RHO0);
+  float rho = PCF(129) * pr;
+  const float dh = PCF(130) - h;
+  // exp(g/R * sat(11000-h) / T): the saturation makes the factor exactly 1 below the tropopause, so it is
+  // evaluated unconditionally (2 MUFU + 4 FP32 ops) instead of behind a divergent branch -- a third of the
+  // environments start within 3 km of 11 km
+  rho *= ex2_fast(fminf(fmaxf(dh, PCF(132)), PCF(131)) * (PCF(133) * 1.4426950408889634f) * rcp_fast(T));
+  const float rV2 = rho * V2;
+  const float qS = rV2 * mp.half_S;
+  const float mD = PCF(126) * CXa * qS;
+  const float Lf = qS * CYa;
+  const float Fx = fmaf(mD, ca, fmaf(sa, Lf, mp.P));
+  const float Fy = fmaf(ca, Lf, -mD * sa);
   // actuator: transport delay (3 steps) -> discrete filter (every 5th tick) -> rate limiter -> saturation
   float td;
   if (stage == 0) td = n > 3 ? r.uh[1] : PCF(137);
@@ -162,8 +318,7 @@ __device__ __forceinline__ void pass32(const float* __restrict__ sP, const float
   float yv = r.df_y;
   if (!(major && n == 0)) {
     const float dT = (stage == 1 || stage == 2) ? 0.005f : 0.01f;
-    float rate = yv - r.rl_prev;
-    yv = r.rl_prev + fminf(fmaxf(rate, dT * PCF(143)), dT * PCF(142));
+    yv = r.rl_prev + fminf(fmaxf(yv - r.rl_prev, dT * PCF(143)), dT * PCF(142));
   }
   o.rl_out = yv;
   o.deltaz_RP = satf(yv, PCF(145), PCF(144));
@@ -178,36 +333,40 @@ __device__ __forceinline__ void pass32(const float* __restrict__ sP, const float
     cs_d = (e_h * c.mp.PID_CS[2] - csf) * c.mp.PID_CS[3];
     cs_pre = e_h * c.mp.PID_CS[0] + csi + cs_d;
     vzh_d = fmin(fmax(cs_pre, Pc(4)), Pc(6));
-    o.vartheta_zh = (float)vzh_d;
+    o.vartheta_zh = __double2float_rn(vzh_d);
   } else {
     o.vartheta_zh = 0.f;
   }
   // pitch error in float64
-  double vref_d = (GEN && use_cs >= PCF(146)) ? vzh_d : r.vartheta;
-  double dv_d = vref_d - th_fold;
+  const double vref_d = (GEN && use_cs >= PCF(146)) ? vzh_d : r.vartheta;
+  const double dv_d = vref_d - th_fold;
   o.dv = dv_d;
-  float dv = (float)dv_d;
+  const float dv = __double2float_rn(dv_d);
+  o.dvf = dv;
   // СС PID
-  float ss_d = (dv * mp.PID_SS[2] - ssf) * mp.PID_SS[3];
-  float ss_pre = fmaf(dv, mp.PID_SS[0], ssi) + ss_d;
+  const float ss_d = (dv * mp.PID_SS[2] - ssf) * mp.PID_SS[3];
+  const float ss_pre = fmaf(dv, mp.PID_SS[0], ssi) + ss_d;
   o.U_com_PID = satf(ss_pre, PCF(5), PCF(7));
   if (mp.use_RL >= PCF(148)) o.U_com = PCF(147) > fabsf(o.U_com_PID) ? 0.f : o.U_com_PID;
   else o.U_com = mp.use_PID_SS >= PCF(9) ? o.U_com_PID : r.deltaz;
-  float ax = (Fx * cs - sn * Fy) * mp.inv_m0;
-  float ay = fmaf(fmaf(Fy, cs, Fx * sn), mp.inv_m0, -mp.g);
-  float dze = mp.use_RP >= PCF(149) ? o.deltaz_RP : o.U_com;
-  float Cm = fmaf(PCF(217) * dCm * Ka, dze * PCF(150), mz);
-  float wzd = Cm * (rV2 * mp.half_Sc_over_Iz);
+  const float ax = (Fx * cs - sn * Fy) * mp.inv_m0;
+  const float ay = fmaf(fmaf(Fy, cs, Fx * sn), mp.inv_m0, -mp.g);
+  const float dze = mp.use_RP >= PCF(149) ? o.deltaz_RP : o.U_com;
+  const float Cm = fmaf(PCF(217) * dCm * Ka, dze * PCF(150), mz);
+  const float wzd = Cm * (rV2 * mp.half_Sc_over_Iz);
   // clamping anti-windup (СС)
-  float dz = ss_pre - satf(ss_pre, PCF(5), PCF(7));
+  const float dz = ss_pre - o.U_com_PID;
   float ss_i = mp.PID_SS[1] * dv;
-  o.and_ss = (ss_pre * PCF(291) != dz) && (sgnf(dz) == sgnf(ss_i));
+  if (PCF(291) == 0.f)  // ZeroGain: ss_pre*0 != dz  <=>  dz != 0 (finite ss_pre); sign(dz)==sign(ss_i) via the sign bits
+    o.and_ss = (dz != 0.f) & (ss_i != 0.f) & ((__float_as_int(dz) ^ __float_as_int(ss_i)) >= 0);
+  else
+    o.and_ss = (ss_pre * PCF(291) != dz) && (sgnf(dz) == sgnf(ss_i));
   if (major) memout_ss = (r.flags & FL_MEM_SS) != 0;
   if (memout_ss) ss_i = PCF(10);
   f_h = Vy; f_Vx = ax; f_Vy = ay; f_wz = wzd; f_ssi = ss_i; f_ssf = ss_d;
-  f_itse = dv_d * dv_d * t_d;
+  f_itse = dv * dv * t_f;
   if (GEN) {
-    double dzc = cs_pre - vzh_d;
+    const double dzc = cs_pre - vzh_d;
     double cs_i = e_h * c.mp.PID_CS[1];
     o.and_cs = (cs_pre * Pc(292) != dzc) && (((dzc > 0.0) - (dzc < 0.0)) == ((cs_i > 0.0) - (cs_i < 0.0)));
     if (major) memout_cs = (r.flags & FL_MEM_CS) != 0;
@@ -221,26 +380,32 @@ __device__ __forceinline__ void pass32(const float* __restrict__ sP, const float
 // model_simple_step in the mixed formulation.  On return r holds the post-update state, `o` the
 // stage-4 pass and s4 the stage-4 (predictor) state values.
 template <bool GEN>
-__device__ __forceinline__ void model_step32(const float* __restrict__ sP, const float* __restrict__ sR, const MP32& mp,
-                                             const DevCfg& c, RegsMx& r, PassMx& o, Stage4Mx& s4, bool want_x) {
+__device__ __forceinline__ void model_step32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, RegsMx& r,
+                                             PassMx& o, Stage4Mx& s4, bool want_x) {
   const int n = r.tick;
-  const double t0 = (double)n * kH;
   const float hh = (float)kH, hhalf = 0.5f * (float)kH;
+  const float t0f = (float)n * hh;
   // float32 copies of the accumulated state for the stage evaluations
-  const float y_h = (float)r.h, y_Vx = (float)r.Vx, y_Vy = (float)r.Vy, y_wz = (float)r.wz, y_ssi = (float)r.ssi,
-              y_ssf = (float)r.ssf;
+  const float y_h = __double2float_rn(r.h), y_Vx = __double2float_rn(r.Vx), y_Vy = __double2float_rn(r.Vy),
+              y_wz = __double2float_rn(r.wz), y_ssi = __double2float_rn(r.ssi), y_ssf = __double2float_rn(r.ssf);
   float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf;
   double X_th = r.th, Xd_h = r.h, X_csi = r.csi, X_csf = r.csf;
   float a_h = 0, a_Vx = 0, a_Vy = 0, a_wz = 0, a_ssi = 0, a_ssf = 0, a_th = 0, a_x = 0;
-  double a_dvi = 0, a_itse = 0, a_csi = 0, a_csf = 0;
+  float a_dvi = 0, a_itse = 0;
+  double a_csi = 0, a_csf = 0;
   bool memout_ss = false, memout_cs = false;
   float u_n = 0.f;
+#if B747_UNROLL_STAGES
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int s = 0; s < 4; s++) {
-    const double t_d = s == 0 ? t0 : (s == 3 ? (double)(n + 1) * kH : t0 + 0.5 * kH);
-    float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf;
-    double f_itse, f_csi, f_csf;
-    pass32<GEN>(sP, sR, mp, c, s, n, X_th, t_d, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, memout_ss,
+    const bool ends = (s == 0 || s == 3);
+    const float t_f = s == 0 ? t0f : (s == 3 ? t0f + hh : t0f + hhalf);
+    float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_itse;
+    double f_csi, f_csf;
+    pass32<GEN>(sT, mp, c, s, n, X_th, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, memout_ss,
                 memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
     if (s == 0) {
       // update(): discrete filter, rate-limiter memory, Memory blocks, Derivative history, delay push
@@ -249,29 +414,31 @@ __device__ __forceinline__ void model_step32(const float* __restrict__ sP, const
       r.flags = (r.flags & ~(FL_MEM_SS | FL_MEM_CS)) | (o.and_ss ? FL_MEM_SS : 0) | (o.and_cs ? FL_MEM_CS : 0);
       const double dvdt_major = n >= 1 ? (o.dv - r.d1_u) * 100.0 : 0.0;
       r.d1_u = o.dv;
-      r.d2_u = (float)dvdt_major;
+      r.d2_u = __double2float_rn(dvdt_major);
       u_n = o.U_com;
     }
-    const float w = (s == 0 || s == 3) ? 1.f : 2.f;
+    const float w = ends ? 1.f : 2.f;
+    const double wd = ends ? 1.0 : 2.0;
     a_h = fmaf(w, f_h, a_h); a_Vx = fmaf(w, f_Vx, a_Vx); a_Vy = fmaf(w, f_Vy, a_Vy); a_wz = fmaf(w, f_wz, a_wz);
     a_ssi = fmaf(w, f_ssi, a_ssi); a_ssf = fmaf(w, f_ssf, a_ssf); a_th = fmaf(w, X_wz, a_th);
-    if (GEN) { a_csi = fma((double)w, f_csi, a_csi); a_csf = fma((double)w, f_csf, a_csf); }
+    if (GEN) { a_csi = fma(wd, f_csi, a_csi); a_csf = fma(wd, f_csf, a_csf); }
     if (want_x) a_x = fmaf(w, X_Vx, a_x);
-    a_dvi = fma((double)w, o.dv, a_dvi);
-    a_itse = fma((double)w, f_itse, a_itse);
+    a_dvi = fmaf(w, o.dvf, a_dvi);
+    a_itse = fmaf(w, f_itse, a_itse);
     if (s < 3) {
       const float cf = (s == 2) ? hh : hhalf;
+      const double cfd = (s == 2) ? kH : 0.5 * kH;
       if (s == 2) {  // integral / position signals at stage 4 = y + h*f2
-        s4.dvi = fma((double)hh, o.dv, r.dvi);
-        s4.itse = fma((double)hh, f_itse, r.itse);
+        s4.dvi = fma(kH, o.dv, r.dvi);
+        s4.itse = r.itse + (double)(hh * f_itse);
         s4.x = want_x ? (float)r.x + hh * X_Vx : 0.f;
       }
-      X_th = fma((double)cf, (double)X_wz, r.th);  // theta' = wz (stage value)
+      X_th = fma(cfd, (double)X_wz, r.th);  // theta' = wz (stage value)
       X_h = fmaf(cf, f_h, y_h); X_Vx = fmaf(cf, f_Vx, y_Vx); X_Vy = fmaf(cf, f_Vy, y_Vy); X_wz = fmaf(cf, f_wz, y_wz);
       X_ssi = fmaf(cf, f_ssi, y_ssi); X_ssf = fmaf(cf, f_ssf, y_ssf);
       if (GEN) {
-        X_csi = fma((double)cf, f_csi, r.csi); X_csf = fma((double)cf, f_csf, r.csf);
-        Xd_h = fma((double)cf, (double)f_h, r.h);
+        X_csi = fma(cfd, f_csi, r.csi); X_csf = fma(cfd, f_csf, r.csf);
+        Xd_h = fma(cfd, (double)f_h, r.h);
       }
     }
   }
@@ -282,8 +449,8 @@ __device__ __forceinline__ void model_step32(const float* __restrict__ sP, const
   r.ssi += (double)(h6 * a_ssi); r.ssf += (double)(h6 * a_ssf); r.th += (double)(h6 * a_th);
   if (GEN) { r.csi = fma(h6d, a_csi, r.csi); r.csf = fma(h6d, a_csf, r.csf); }
   if (want_x) r.x += (double)(h6 * a_x);
-  r.dvi = fma(h6d, a_dvi, r.dvi);
-  r.itse = fma(h6d, a_itse, r.itse);
+  r.dvi += (double)(h6 * a_dvi);
+  r.itse += (double)(h6 * a_itse);
   r.uh[0] = r.uh[1]; r.uh[1] = r.uh[2]; r.uh[2] = r.uh[3]; r.uh[3] = u_n;
   r.tick = n + 1;
 }

@@ -25,7 +25,7 @@ def E():
     return engine
 
 
-def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=None):
+def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=None, sticky=0):
     """Step engine and oracle in lock-step with the same actions; returns the worst deviations."""
     cfg_o = O.make_cfg(seed=seed, **kw)
     eng = E.BatchEngine(n_envs=n, dtype=dtype, seed=seed, auto_reset=True, **kw)
@@ -36,10 +36,14 @@ def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=N
     rng = np.random.default_rng(seed)
     amax = 1.0 if cfg_o.norm_act else cfg_o.action_max
     worst_o = worst_r = 0.0
+    env_worst = np.zeros(n)
     term = np.zeros((n, eng.obs_dim), eng.np_dtype)
     n_done = 0
     for k in range(steps):
-        a = rng.uniform(-amax, amax, n).astype(eng.np_dtype)
+        if sticky and k % sticky:
+            pass  # hold the previous action: drives the airframe far out of the trimmed envelope
+        else:
+            a = rng.uniform(-amax, amax, n).astype(eng.np_dtype)
         obs, rew, done, term = eng.step_host(a, terminal_obs=term)
         o_o, r_o, d_o, t_o = ob.step(a.astype(np.float64))
         assert np.array_equal(done.astype(bool), d_o), f"done flags differ at step {k}"
@@ -52,8 +56,10 @@ def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=N
         assert (eo <= obs_tol[0] + obs_tol[1] * np.abs(o_o)).all(), f"step {k}: obs deviation {eo.max():.3e}"
         assert (er <= rew_tol).all(), f"step {k}: reward deviation {er.max():.3e}"
         worst_o, worst_r = max(worst_o, et.max()), max(worst_r, er.max())
+        env_worst = np.maximum(env_worst, et.max(axis=1))
     st = eng.episode_stats()
     assert st[0] == n_done
+    eng.env_worst = env_worst
     return worst_o, worst_r, n_done, eng
 
 
@@ -116,6 +122,22 @@ def test_f32_bound_over_1000_steps(E, oracle):
         print(f"f32 K={K} {n}x1000: max|dobs|={wo:.2e} max|drew|={wr:.2e}")
 
 
+def test_f32_far_envelope_rare_paths(E, oracle):
+    """Elevator commands held for 2..20 s put environments at high angles of attack, beyond +-90 deg of pitch
+    (the DLL's asin fold) and above the tropopause: every fall-back of the f32 path (libm trigonometry outside the
+    polynomial ranges, table interval re-searches, pitch fold) is exercised.  Trajectories that tumble are
+    sensitive to rounding (an airframe tumbling through the stall amplifies a 1e-7 difference a thousandfold within
+    seconds), so the bar is two-fold: the median environment stays inside the canonical 1e-5, the worst tumbling one
+    inside 2e-2 (measured round 1: median 1.5e-7, p99 2.9e-3, max 4.9e-3 with the elevator held for a whole episode)."""
+    for K, n, hold in ((10, 512, 200), (5, 512, 40)):
+        wo, wr, nd, eng = _rollout_compare(E, oracle, E.F32, n, 420, dict(sample_time=K * 0.01), 33, (2e-2, 0.0), 5e-2,
+                                           sticky=hold)
+        q = np.quantile(eng.env_worst, [0.5, 0.9, 0.99])
+        print(f"f32 far-envelope K={K} hold={hold}: max|dobs|={wo:.2e} max|drew|={wr:.2e}; per-env worst |dobs| "
+              f"median {q[0]:.1e} p90 {q[1]:.1e} p99 {q[2]:.1e}")
+        assert q[0] <= 1e-5   # the typical environment stays inside the canonical bound
+
+
 @pytest.mark.parametrize("name", sorted(VARIANTS))
 def test_f32_variants_within_bound(E, oracle, name):
     kw = VARIANTS[name]
@@ -135,6 +157,8 @@ def test_full_size_properties_config3(E, oracle):
     n, K = 1 << 20, 10
     kw = dict(sample_time=K * 0.01)
     eng = E.BatchEngine(n_envs=n, dtype=E.F32, seed=1, **kw)
+    # both handles launch on torch's current stream, so the action generation / slicing below is ordered with the steps
+    eng.use_stream(torch.cuda.current_stream().cuda_stream)
     act, obs, rew, done = eng.alloc_io()
     eng.reset(obs)
     eng.synchronize()
@@ -143,6 +167,7 @@ def test_full_size_properties_config3(E, oracle):
     # sharding invariance: a 4096-env handle holding the same GLOBAL env ids gives bit-identical results
     lo = 777 * 128
     sl = E.BatchEngine(n_envs=4096, dtype=E.F32, seed=1, env_id_offset=lo, **kw)
+    sl.use_stream(torch.cuda.current_stream().cuda_stream)
     a2, o2, r2, d2 = sl.alloc_io()
     sl.reset(o2)
     # oracle on 512 of those envs
@@ -157,7 +182,9 @@ def test_full_size_properties_config3(E, oracle):
         sl.step(a2, o2, r2, d2)
         eng.synchronize(); sl.synchronize()
         assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
-        assert float(rew.min()) >= -0.2 and float(rew.max()) <= 1.0 + 1e-6   # CLASSIC reward range
+        # CLASSIC reward range: r1..r4 in (0, 1]; rf >= -kf * (|dvartheta| / (2 |vf|)) with the folded pitch error
+        # below 100 deg and |vf| >= 1 deg (env/ctrl_env.py:124-143)
+        assert float(rew.min()) >= -5.0 and float(rew.max()) <= 1.0 + 1e-6
         assert torch.equal(obs[lo:lo + 4096], o2) and torch.equal(rew[lo:lo + 4096], r2)
         assert torch.equal(done[lo:lo + 4096], d2)
         nd = int(done.sum())
@@ -183,6 +210,7 @@ def test_full_size_properties_config3(E, oracle):
     outs = []
     for _ in range(2):
         e2 = E.BatchEngine(n_envs=n, dtype=E.F32, seed=1, **kw)
+        e2.use_stream(torch.cuda.current_stream().cuda_stream)
         b_act, b_obs, b_rew, b_done = e2.alloc_io()
         e2.reset(b_obs)
         b_act.uniform_(-1, 1, generator=torch.Generator(device="cuda").manual_seed(0))
