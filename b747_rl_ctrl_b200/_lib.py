@@ -88,6 +88,7 @@ def load():
     L.b747_launch_count.restype = ctypes.c_int64
     L.b747_launch_count.argtypes = [vp]
     L.b747_synchronize.argtypes = [vp]
+    L.b747_selftest_tables.argtypes = [c_int, c_int, c_dp]
     L.b747_philox4x32.argtypes = [ctypes.POINTER(ctypes.c_uint32)] * 3
     _lib = L
     return L

@@ -26,7 +26,7 @@ UNITS = {
     "b747_capi.cu": [],
     "b747_scalar.cu": [],
 }
-HEADERS = ["b747_common.cuh", "b747_kernels.h", "b747_model_f64.cuh", "b747_model_mx.cuh", "b747_poly.h",
+HEADERS = ["b747_common.cuh", "b747_kernels.h", "b747_model_f64.cuh", "b747_model_mx.cuh", "b747_poly.h", "b747_tables.h",
            "../../include/b747.h", "../../include/b747_params.h", "../../include/b747_scalar.h"]
 
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "b747_kernels.h"
+#include "b747_tables.h"
 
 using namespace b747;
 
@@ -87,6 +88,30 @@ const std::vector<FieldDesc>& fields() {
   return f;
 }
 }  // namespace
+
+extern "C" int b747_selftest_tables(int n_points, int extrapolate, double out[5]) {
+  const b747::ft::Fast F = b747::ft::build();
+  if (!F.ok || !out) return fail(B747_ERR_STATE, "model_simple_P does not fit the compiled table layout");
+  const b747::ft::Orig O;
+  const b747::ft::FastEval E{F};
+  const double scale[5] = {1.0, 0.1, 0.02, 0.3, 1.0};
+  for (int j = 0; j < 5; j++) out[j] = 0.0;
+  uint32_t key[2] = {0x747u, 0u};
+  for (int k = 0; k < n_points; k++) {
+    uint32_t ctr[4] = {(uint32_t)k, 0u, 0u, 0u}, w[4];
+    b747::philox4x32(ctr, key, w);
+    const double u0 = w[0] / 4294967296.0, u1 = w[1] / 4294967296.0, u2 = w[2] / 4294967296.0;
+    const double M = extrapolate ? -0.1 + 1.4 * u0 : 0.1 + 0.95 * u0;
+    const double a = extrapolate ? -40.0 + 100.0 * u1 : -10.0 + 45.0 * u1;
+    const double h = extrapolate ? -2000.0 + 18000.0 * u2 : 12500.0 * u2;
+    double o[5];
+    E.eval(M, a, h, o);
+    const double cy = O.CYa(M, a);
+    const double r[5] = {cy, O.CXa(M, cy), O.dCm(h, M), O.mz(M, a), O.Ka(a)};
+    for (int j = 0; j < 5; j++) out[j] = fmax(out[j], fabs(o[j] - r[j]) / (fabs(r[j]) + scale[j]));
+  }
+  return B747_OK;
+}
 
 extern "C" int b747_n_fields(void) { return (int)fields().size(); }
 extern "C" const char* b747_field_name(int i) { return (i >= 0 && i < (int)fields().size()) ? fields()[i].name : nullptr; }

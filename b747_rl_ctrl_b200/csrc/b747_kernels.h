@@ -28,6 +28,7 @@ struct StateF32 {
   double* stats = nullptr;
   double* last_ret = nullptr;
   int* last_len = nullptr;
+  float4* tables = nullptr;  // merged-axis look-up tables (b747_tables.h), ft::CELLS float4
 };
 
 int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t stream);

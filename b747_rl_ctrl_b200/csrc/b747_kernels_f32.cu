@@ -140,11 +140,8 @@ __device__ __forceinline__ float nan_to_num_f(float x) {
   return x;
 }
 
-// look-up tables in the fast path's layout, built at compile time (b747_model_mx.cuh)
-__device__ const FastTables gFastTables = make_fast_tables();
-
-__device__ __forceinline__ void load_tables32(float4* sT) {
-  const float4* g = reinterpret_cast<const float4*>(gFastTables.v);
+// look-up tables in the fast path's layout (b747_tables.h; built on the host at handle creation): HBM/L2 -> shared
+__device__ __forceinline__ void load_tables32(float4* sT, const float4* __restrict__ g) {
   for (int k = threadIdx.x; k < kFastCells; k += blockDim.x) sT[k] = g[k];
   __syncthreads();
 }
@@ -159,7 +156,7 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
                                                     uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
   __shared__ float4 sT[kFastCells];
   __shared__ EpStatsSmem sst;
-  load_tables32(sT);
+  load_tables32(sT, st.tables);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < c.n_envs;
   const size_t np = (size_t)c.n_pad;
@@ -389,6 +386,12 @@ int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t st
   if (cudaMalloc(&s.stats, sizeof(double) * 4) != cudaSuccess) return -1;
   if (cudaMalloc(&s.last_ret, sizeof(double) * np) != cudaSuccess) return -1;
   if (cudaMalloc(&s.last_len, sizeof(int) * np) != cudaSuccess) return -1;
+  {
+    const ft::Fast F = ft::build();
+    if (!F.ok) return -2;  // model_simple_P does not fit the compiled table layout
+    if (cudaMalloc(&s.tables, sizeof(float4) * ft::CELLS) != cudaSuccess) return -1;
+    if (cudaMemcpy(s.tables, F.v.data(), sizeof(float4) * ft::CELLS, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  }
   cudaMemsetAsync(s.D, 0, sizeof(double2) * np * ND_GROUPS, stream);
   cudaMemsetAsync(s.F, 0, sizeof(float4) * np * NF_GROUPS, stream);
   cudaMemsetAsync(s.stats, 0, sizeof(double) * 4, stream);
@@ -396,7 +399,7 @@ int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t st
 }
 
 void f32_free(StateF32& s) {
-  cudaFree(s.D); cudaFree(s.F); cudaFree(s.sig); cudaFree(s.stats); cudaFree(s.last_ret); cudaFree(s.last_len);
+  cudaFree(s.D); cudaFree(s.F); cudaFree(s.sig); cudaFree(s.stats); cudaFree(s.last_ret); cudaFree(s.last_len); cudaFree(s.tables);
   s = StateF32{};
 }
 

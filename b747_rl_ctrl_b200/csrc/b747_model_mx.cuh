@@ -15,11 +15,12 @@
 //    so these ~10 operations per pass are nearly free;
 //  * every integrator state is accumulated in float64 across steps (y += h/6 * sum), the stage
 //    values inside a step are float32;
-//  * look-ups: per axis ONE 128-bit shared-memory load returns {valid-lo, valid-hi, breakpoint,
-//    1/spacing} of the cached interval; the cached interval index is validated with two compares
-//    and only re-searched (incrementally) when the operand left the interval -- Mach, alpha and h
-//    move by ~1e-4 of an interval per pass.  Each 2-D table cell is one 128-bit load of
-//    {t00, t10-t00, t01, t11-t01};
+//  * look-ups: the five tables are re-sampled on merged axes (b747_tables.h: one Mach, one alpha, one
+//    altitude and one CYa axis instead of the DLL's eight breakpoint sets -- exact for a bilinear
+//    interpolant).  Per axis ONE 128-bit shared-memory load returns {valid-lo, valid-hi, breakpoint,
+//    1/spacing} of the cached interval; the cached interval is validated with two compares and only
+//    re-searched (incrementally) when the operand left it -- Mach, alpha and h move by ~1e-4 of an
+//    interval per pass.  Each 2-D table cell is one 128-bit load of {t00, t10-t00, t01, t11-t01};
 //  * sin/cos(theta), atan(wb/ub) and the ISA density power are short float32 polynomials
 //    (b747_poly.h, generated + validated by tools/gen_poly.py) with libm fall-backs outside their
 //    fitted ranges; sin(alpha), cos(alpha) come from the body-axis velocity components;
@@ -32,6 +33,7 @@
 
 #include "b747_common.cuh"
 #include "b747_poly.h"
+#include "b747_tables.h"
 
 #ifndef B747_UNROLL_STAGES
 #define B747_UNROLL_STAGES 1  // 1: the four diagram passes of a model step are specialised copies; 0: one rolled loop
@@ -51,72 +53,11 @@ struct PF { static constexpr float v = (float)Pc(I); };
 // fitted range always covers it
 static_assert((Pc(16) - Pc(17) * Pc(19)) * Pc(127) > 0.70 && (Pc(16) - Pc(18) * Pc(19)) * Pc(127) < 1.01,
               "ISA temperature ratio leaves the range of the density polynomial (tools/gen_poly.py)");
-static_assert(Pc(42) == Pc(276) && Pc(43) == Pc(277) && Pc(44) == Pc(278) && Pc(45) == Pc(279),
-              "CYa and mz are expected to share their Mach breakpoints");
 
-// ---------------------------------------------------------------------------------------------
-// Look-up tables in the layout the fast path reads (built at compile time from model_simple_P).
-// Axis a, interval i (0..M-1):  {lo, hi, bp[i], 1/(bp[i+1]-bp[i])}; lo of the first and hi of the last
-// interval are NaN, so that `u < lo || u >= hi` is false there (end intervals extrapolate, like
-// look2_binlx) and false for a NaN operand (the search then keeps its interval instead of running away).
-// ---------------------------------------------------------------------------------------------
-enum { AX_Ma = 0, AX_Aa, AX_Mb, AX_C, AX_H, AX_Mc, AX_Ac, AX_Ab, N_AXES };
-struct AxisDef { int base, M; };
-__host__ __device__ constexpr AxisDef axis_def(int a) {
-  constexpr AxisDef d[N_AXES] = {{42, 3}, {46, 4}, {108, 3}, {112, 13}, {201, 4}, {206, 9}, {225, 6}, {280, 10}};
-  return d[a];
-}
-__host__ __device__ constexpr int axis_off(int a) {  // float4 index of axis a's first interval
-  int o = 0;
-  for (int k = 0; k < a; k++) o += axis_def(k).M;
-  return o;
-}
-constexpr int kAxisCells = axis_off(N_AXES);  // 52
-enum { TB_CYa = 0, TB_CXa, TB_dCm, TB_mz, N_TABS };
-struct TabDef { int base, ax0, ax1, stride; };
-__host__ __device__ constexpr TabDef tab_def(int t) {
-  constexpr TabDef d[N_TABS] = {{22, AX_Ma, AX_Aa, 4}, {52, AX_Mb, AX_C, 4}, {151, AX_H, AX_Mc, 5}, {232, AX_Ma, AX_Ab, 4}};
-  return d[t];
-}
-__host__ __device__ constexpr int tab_off(int t) {  // float4 index of table t's first cell
-  int o = kAxisCells;
-  for (int k = 0; k < t; k++) o += axis_def(tab_def(k).ax0).M * axis_def(tab_def(k).ax1).M;
-  return o;
-}
-constexpr int kKaOff = tab_off(N_TABS);                 // K_alpha: {t[i], t[i+1]-t[i], -, -} per interval
-constexpr int kFastCells = kKaOff + axis_def(AX_Ac).M;  // float4 count
-
-struct FastTables { float v[kFastCells * 4]; };
-constexpr FastTables make_fast_tables() {
-  FastTables T{};
-  const float qnan = __builtin_nanf("");
-  for (int a = 0; a < N_AXES; a++) {
-    const AxisDef d = axis_def(a);
-    for (int i = 0; i < d.M; i++) {
-      float* q = T.v + (axis_off(a) + i) * 4;
-      q[0] = i == 0 ? qnan : (float)Pc(d.base + i);
-      q[1] = i == d.M - 1 ? qnan : (float)Pc(d.base + i + 1);
-      q[2] = (float)Pc(d.base + i);
-      q[3] = (float)(1.0 / (Pc(d.base + i + 1) - Pc(d.base + i)));
-    }
-  }
-  for (int t = 0; t < N_TABS; t++) {
-    const TabDef d = tab_def(t);
-    const int M0 = axis_def(d.ax0).M, M1 = axis_def(d.ax1).M;
-    for (int i1 = 0; i1 < M1; i1++)
-      for (int i0 = 0; i0 < M0; i0++) {
-        float* q = T.v + (tab_off(t) + i1 * M0 + i0) * 4;
-        const int o = d.base + i1 * d.stride + i0;
-        q[0] = (float)Pc(o); q[1] = (float)(Pc(o + 1) - Pc(o));
-        q[2] = (float)Pc(o + d.stride); q[3] = (float)(Pc(o + d.stride + 1) - Pc(o + d.stride));
-      }
-  }
-  for (int i = 0; i < axis_def(AX_Ac).M; i++) {
-    float* q = T.v + (kKaOff + i) * 4;
-    q[0] = (float)Pc(218 + i); q[1] = (float)(Pc(218 + i + 1) - Pc(218 + i)); q[2] = 0.f; q[3] = 0.f;
-  }
-  return T;
-}
+// Look-up tables: re-gridded on merged axes by the host (b747_tables.h), staged in shared memory.
+enum { AX_M = 0, AX_A, AX_H, AX_C, N_AXES };
+__host__ __device__ constexpr int axis_off(int a) { return a == AX_M ? ft::AXM : a == AX_A ? ft::AXA : a == AX_H ? ft::AXH : ft::AXC; }
+constexpr int kFastCells = ft::CELLS;
 
 // float copies of the uniform tunables + folded constants (built on the host, b747_kernels_f32.cu)
 struct MP32 {
@@ -201,10 +142,8 @@ __device__ __forceinline__ float4 axis_peek(const float4* __restrict__ sT, int o
 }
 __device__ __forceinline__ bool axis_miss(float u, const float4& q) { return (u < q.x) | (u >= q.y); }
 
-template <int T>
-__device__ __forceinline__ float table2(const float4* __restrict__ sT, int off0, float f0, int off1, float f1) {
-  constexpr int M0 = axis_def(tab_def(T).ax0).M;
-  const float4 c = *(const float4*)((const char*)(sT + tab_off(T)) + off1 * M0 + off0);
+// bilinear cell {t00, t10-t00, t01, t11-t01}: look2_binlx's operation order with the differences pre-computed
+__device__ __forceinline__ float bilinear(const float4 c, float f0, float f1) {
   const float yL = fmaf(c.y, f0, c.x);
   const float yR = fmaf(c.w, f0, c.z);
   return fmaf(yR - yL, f1, yL);
@@ -256,40 +195,31 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   const float Mach = V * rsqrt_fast(T * PCF(20));
   const float ad = alpha * PCF(21);
   o.Mach = Mach;
-  // look-ups.  Fast path: load the cached interval record of every axis whose operand is already known
-  // (7 x LDS.128), validate all of them with one combined predicate and branch once; the re-search of an
-  // axis that left its interval is rare (Mach, alpha, h move ~1e-4 of an interval per pass).
-  float fMa, fAa, fMb, fH, fMc, fAc, fAb;
-  bool miss;
-  {
-    float4 q;
-    q = axis_peek<AX_Ma>(sT, r.ax[AX_Ma]); miss = axis_miss(Mach, q); fMa = (Mach - q.z) * q.w;
-    q = axis_peek<AX_Aa>(sT, r.ax[AX_Aa]); miss |= axis_miss(ad, q); fAa = (ad - q.z) * q.w;
-    q = axis_peek<AX_Mb>(sT, r.ax[AX_Mb]); miss |= axis_miss(Mach, q); fMb = (Mach - q.z) * q.w;
-    q = axis_peek<AX_H>(sT, r.ax[AX_H]); miss |= axis_miss(h, q); fH = (h - q.z) * q.w;
-    q = axis_peek<AX_Mc>(sT, r.ax[AX_Mc]); miss |= axis_miss(Mach, q); fMc = (Mach - q.z) * q.w;
-    q = axis_peek<AX_Ac>(sT, r.ax[AX_Ac]); miss |= axis_miss(ad, q); fAc = (ad - q.z) * q.w;
-    q = axis_peek<AX_Ab>(sT, r.ax[AX_Ab]); miss |= axis_miss(ad, q); fAb = (ad - q.z) * q.w;
-    if (miss) {  // rare: some operand left its cached interval -> incremental re-search
-      q = axis_lookup<AX_Ma>(sT, Mach, r.ax[AX_Ma]); fMa = (Mach - q.z) * q.w;
-      q = axis_lookup<AX_Aa>(sT, ad, r.ax[AX_Aa]); fAa = (ad - q.z) * q.w;
-      q = axis_lookup<AX_Mb>(sT, Mach, r.ax[AX_Mb]); fMb = (Mach - q.z) * q.w;
-      q = axis_lookup<AX_H>(sT, h, r.ax[AX_H]); fH = (h - q.z) * q.w;
-      q = axis_lookup<AX_Mc>(sT, Mach, r.ax[AX_Mc]); fMc = (Mach - q.z) * q.w;
-      q = axis_lookup<AX_Ac>(sT, ad, r.ax[AX_Ac]); fAc = (ad - q.z) * q.w;
-      q = axis_lookup<AX_Ab>(sT, ad, r.ax[AX_Ab]); fAb = (ad - q.z) * q.w;
-    }
+  // look-ups on the merged axes (b747_tables.h): one cached interval per operand.  Fast path: three
+  // LDS.128 fetch the cached interval records, one combined predicate validates them; the incremental
+  // re-search of an operand that left its interval is rare (Mach, alpha, h move ~1e-4 of an interval per pass).
+  float4 qM = axis_peek<AX_M>(sT, r.ax[AX_M]);
+  float4 qA = axis_peek<AX_A>(sT, r.ax[AX_A]);
+  float4 qH = axis_peek<AX_H>(sT, r.ax[AX_H]);
+  if (axis_miss(Mach, qM) | axis_miss(ad, qA) | axis_miss(h, qH)) {
+    qM = axis_lookup<AX_M>(sT, Mach, r.ax[AX_M]);
+    qA = axis_lookup<AX_A>(sT, ad, r.ax[AX_A]);
+    qH = axis_lookup<AX_H>(sT, h, r.ax[AX_H]);
   }
-  float CYa = table2<TB_CYa>(sT, r.ax[AX_Ma], fMa, r.ax[AX_Aa], fAa);
+  const float fM = (Mach - qM.z) * qM.w, fA = (ad - qA.z) * qA.w, fH = (h - qH.z) * qH.w;
+  const char* sB = (const char*)sT;
+  // CYa and mz share the (Mach, alpha) cell: two adjacent 128-bit loads
+  const float4* cMA = (const float4*)(sB + ft::T_MA * 16 + (r.ax[AX_A] * ft::NM + r.ax[AX_M]) * 2);
+  float CYa = bilinear(cMA[0], fM, fA);
+  float mz = bilinear(cMA[1], fM, fA);
   if (GEN) CYa *= r.sumA[1];
   const float4 qC = axis_lookup<AX_C>(sT, CYa, r.ax[AX_C]);
-  float CXa = table2<TB_CXa>(sT, r.ax[AX_Mb], fMb, r.ax[AX_C], (CYa - qC.z) * qC.w);
+  float CXa = bilinear(*(const float4*)(sB + ft::T_MC * 16 + r.ax[AX_C] * ft::NM + r.ax[AX_M]), fM, (CYa - qC.z) * qC.w);
   if (GEN) CXa *= r.sumA[0];
   o.CYa = CYa; o.CXa = CXa;
-  float dCm = table2<TB_dCm>(sT, r.ax[AX_H], fH, r.ax[AX_Mc], fMc);
-  const float4 kc = *(const float4*)((const char*)(sT + kKaOff) + r.ax[AX_Ac]);
-  float Ka = fmaf(kc.y, fAc, kc.x);
-  float mz = table2<TB_mz>(sT, r.ax[AX_Ma], fMa, r.ax[AX_Ab], fAb);
+  float dCm = bilinear(*(const float4*)(sB + ft::T_HM * 16 + r.ax[AX_M] * ft::NH + r.ax[AX_H]), fH, fM);
+  const float4 kc = *(const float4*)(sB + ft::KA * 16 + r.ax[AX_A]);
+  float Ka = fmaf(kc.y, fA, kc.x);
   if (GEN) { dCm *= r.sumA[3]; Ka *= r.sumA[4]; mz *= r.sumA[2]; }
   o.dCm = dCm; o.K_alpha = Ka; o.mz = mz;
   // density: rho0 * (T/T0)^(g/(LR)-1) [* exp(g/R * sat(11000-h) / T) above the tropopause]

@@ -144,6 +144,12 @@ int b747_last_episode(b747_handle *h, double *ret_host, int32_t *len_host);
 int64_t b747_launch_count(b747_handle *h);
 int b747_synchronize(b747_handle *h);
 
+/* Host-side self-test of the merged-axis look-up tables the f32 kernels read (b747_tables.h): re-samples
+ * model_simple_P, then compares the re-gridded interpolation with look2_binlx / look1 semantics
+ * (dll@0x1000) on n_points pseudo-random operands in float64.  extrapolate != 0 also draws operands far
+ * outside the breakpoint ranges.  out_max_rel_err: CYa, CXa, dCm_ddeltaz, mz, K_alpha.  No GPU needed. */
+int b747_selftest_tables(int n_points, int extrapolate, double out_max_rel_err[5]);
+
 /* Philox4x32-10 as used for resets (exposed for known-answer tests). */
 void b747_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
