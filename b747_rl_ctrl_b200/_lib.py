@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B747_LIB_PATH") or os.path.join(HERE, "lib", "libb747_b200.so")
 SCALAR_LIB_PATH = os.path.join(HERE, "lib", "model_simple.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_STATE = 0, -1, -2, -3, -4
 F64, F32 = 0, 1
 
@@ -33,7 +33,7 @@ class Cfg(ctypes.Structure):
         ("tk", ctypes.c_double), ("action_max", ctypes.c_double), ("vartheta_max", ctypes.c_double),
         ("sample_time", ctypes.c_double), ("rew", ctypes.c_double * 8),
         ("fixed_aero_err", ctypes.c_double * 5), ("has_fixed_aero_err", ctypes.c_int32),
-        ("export_signals", ctypes.c_int32),
+        ("export_signals", ctypes.c_int32), ("track_transfer", ctypes.c_int32), ("record_capacity", ctypes.c_int32),
     ]
 
 
@@ -88,6 +88,11 @@ def load():
     L.b747_launch_count.restype = ctypes.c_int64
     L.b747_launch_count.argtypes = [vp]
     L.b747_synchronize.argtypes = [vp]
+    L.b747_transfer_metrics.argtypes = [vp, c_int, c_int, vp]
+    L.b747_recorder_n_fields.restype = c_int
+    L.b747_recorder_field_name.restype = ctypes.c_char_p
+    L.b747_recorder_field_name.argtypes = [c_int]
+    L.b747_recorder_read.argtypes = [vp, c_int, vp, ctypes.POINTER(ctypes.c_int32)]
     L.b747_selftest_tables.argtypes = [c_int, c_int, c_dp]
     L.b747_philox4x32.argtypes = [ctypes.POINTER(ctypes.c_uint32)] * 3
     _lib = L

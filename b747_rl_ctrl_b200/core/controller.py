@@ -12,6 +12,7 @@ from math import exp, pi
 import numpy as np
 
 from .. import engine as E
+from ..tools.general import Storage, calc_err, calc_stepinfo
 from .model import ModelView
 
 
@@ -37,17 +38,6 @@ class ResetRefMode(Enum):  # core/controller.py:28-32
 
 class DisturbanceMode(Enum):  # core/controller.py:34-36
     AERO_DISTURBANCE = 0
-
-
-def calc_err(x1, x2):  # tools/general.py:35-43
-    err = x1 - x2
-    if x2 != 0:
-        err /= x2
-    elif x1 != 0:
-        err /= x1
-    else:
-        err = 0
-    return abs(err)
 
 
 def _const_value(func, what):
@@ -87,9 +77,12 @@ class Controller:
         self.action_max = action_max
         self.vartheta_max = vartheta_max
         self.use_limiter = use_limiter
+        # Storage: the kernel records what Controller._post_step records, after every model step
+        # (core/controller.py:209-228), and evaluates calc_stepinfo online; `use_storage` only gates the reads, so
+        # callers may flip it after construction like neural/callbacks.py:66 does.
         self.use_storage = use_storage
-        if use_storage:
-            raise NotImplementedError("Storage recording (tools/general.py Storage) is the next scope row (SURVEY.md 8f N2)")
+        self.storage_backup = Storage()
+        self._K = E._lib.substeps_of(sample_time)
         env = _env or {}
         self._engine = E.BatchEngine(
             n_envs=1, dtype=dtype, device=device,
@@ -100,7 +93,8 @@ class Controller:
             reset_ref_mode=(reset_ref_mode.value if reset_ref_mode is not None else E.RESET_NONE),
             disturbance_mode=(disturbance_mode.value if disturbance_mode is not None else E.DIST_NONE),
             use_limiter=use_limiter, tk=tk, sample_time=sample_time, action_max=action_max, vartheta_max=vartheta_max,
-            aero_err=aero_err, seed=seed, auto_reset=False, env_layer=True, export_signals=True)
+            aero_err=aero_err, seed=seed, auto_reset=False, env_layer=True, export_signals=True,
+            track_transfer=True, record_capacity=self._rec_capacity(tk))
         self.model = ModelView(self._engine, 0)
         self.state_backup = np.zeros(6)
         self._state0 = None
@@ -130,9 +124,22 @@ class Controller:
         if v is not None:
             self._engine.set("href", v)
 
+    def _rec_capacity(self, tk):
+        n = E._lib.done_tick_of(tk)
+        return int(n + self._K) if n < 10 ** 6 else 0  # an unbounded episode (tk = inf) is not recorded
+
+    @property
+    def storage(self):
+        """The running episode's records, one entry per model step (empty unless use_storage)."""
+        if not self.use_storage or not self._engine.cfg.record_capacity:
+            return Storage()
+        return Storage({k: list(v) for k, v in self._engine.recorder_read(0).items() if len(v)})
+
     def reset(self, state0=None):
         """core/controller.py:134-201."""
         eng = self._engine
+        if self.use_storage:  # core/controller.py:195-199
+            self.storage_backup = self.storage
         if state0 is not None and len(state0) > 0:
             state0 = np.asarray(state0, dtype=np.float64)
             assert state0.shape == (6,), "Размерности заданного вектора состояния state0 и вектора состояния модели не совпадают."
@@ -204,6 +211,26 @@ class Controller:
 
     def calc_CS_err(self):
         return calc_err(self.model.state_dict['y'], self.model.hzh)
+
+    def stepinfo_SS(self, use_backup=False):
+        """core/controller.py:346-352.  The running episode is answered by the in-kernel tracker (calc_stepinfo
+        evaluated online, constant reference); a backed-up episode from its recorded arrays."""
+        return self._stepinfo("SS", 'vartheta', 'vartheta_ref', use_backup)
+
+    def stepinfo_CS(self, use_backup=False):
+        """core/controller.py:354-360."""
+        return self._stepinfo("CS", 'y', 'hzh', use_backup)
+
+    def _stepinfo(self, which, sig, ref, use_backup):
+        st = (self.storage_backup if use_backup else self.storage).storage
+        if not self.use_storage or sig not in st or 't' not in st:
+            raise ValueError('Вычисление хар-к ПП недоступно: ошибка хранилища.')
+        const_ref = len(set(st[ref])) == 1
+        if use_backup or not const_ref:
+            return calc_stepinfo(st[sig], st[ref][-1], ts=st['t'])
+        m = self._engine.transfer_metrics(which, finished=False)[0]
+        val = lambda x: None if x != x else float(x)
+        return {'overshoot': val(m[0]), 'static_error': val(m[3]), 'rise_time': val(m[1]), 'settling_time': val(m[2])}
 
     def quality(self):
         """core/controller.py:334-336 (float64 host evaluation of two signals; the in-kernel QUALITY

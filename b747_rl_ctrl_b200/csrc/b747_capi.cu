@@ -1,6 +1,7 @@
 // b747_capi.cu -- the C ABI of libb747_b200.so (include/b747.h).  Host-side glue only: device
 // memory, streams, launches.  There is no CPU implementation behind any entry point.
 #include <math.h>
+#include <algorithm>
 #include <stdio.h>
 #include <string.h>
 
@@ -33,6 +34,8 @@ struct b747_handle {
   void *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_term = nullptr;
   uint8_t* d_done = nullptr;
   b747_episode* d_eps = nullptr;
+  double* d_metrics = nullptr;  // [n_pad][5] staging for b747_transfer_metrics
+  TraceState trace;
   int64_t launches = 0;
   size_t elem() const { return cfg.dtype == B747_F64 ? 8 : 4; }
 };
@@ -177,6 +180,23 @@ extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
   h->own_stream = true;
   const size_t np = (size_t)h->dc.n_pad;
   const int od = h->dc.obs_dim;
+  if (cfg->track_transfer) {
+    CU(cudaMalloc(&h->trace.trk, sizeof(double) * 2 * NTRK * np));
+    CU(cudaMalloc(&h->trace.snap, sizeof(double) * 2 * NTRK * np));
+    CU(cudaMemsetAsync(h->trace.trk, 0, sizeof(double) * 2 * NTRK * np, h->stream));
+    CU(cudaMemsetAsync(h->trace.snap, 0, sizeof(double) * 2 * NTRK * np, h->stream));
+    CU(cudaMalloc(&h->d_metrics, sizeof(double) * 5 * np));
+  }
+  if (cfg->record_capacity > 0) {
+    const size_t bytes = sizeof(double) * (size_t)cfg->record_capacity * NREC * (size_t)cfg->n_envs;
+    if (bytes > ((size_t)8 << 30)) return fail(B747_ERR_ALLOC, "recorder larger than 8 GiB: lower record_capacity or n_envs");
+    CU(cudaMalloc(&h->trace.rec, bytes));
+    CU(cudaMemsetAsync(h->trace.rec, 0, bytes, h->stream));
+    h->trace.rec_cap = cfg->record_capacity;
+    h->trace.rec_stride = cfg->n_envs;
+  }
+  h->s64.trace = h->trace;
+  h->s32.trace = h->trace;
   if (cfg->dtype == B747_F64) {
     StateF64& s = h->s64;
     CU(cudaMalloc(&s.slots, sizeof(double) * np * (NSLOT_F64 + 6)));
@@ -213,6 +233,7 @@ extern "C" int b747_destroy(b747_handle* h) {
   if (!h) return B747_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
+  cudaFree(h->trace.trk); cudaFree(h->trace.snap); cudaFree(h->trace.rec); cudaFree(h->d_metrics);
   StateF64& s = h->s64;
   cudaFree(s.slots); cudaFree(s.tick); cudaFree(s.flags); cudaFree(s.ep_idx); cudaFree(s.sig); cudaFree(s.stats);
   cudaFree(s.last_ret); cudaFree(s.last_len);
@@ -233,6 +254,44 @@ extern "C" int b747_set_stream(b747_handle* h, void* s) {
   return B747_OK;
 }
 extern "C" int64_t b747_launch_count(b747_handle* h) { return h ? h->launches : 0; }
+
+// ---- trace: step-response metrics and recorder ---------------------------------------------------
+extern "C" int b747_transfer_metrics(b747_handle* h, int which, int finished, double* out) {
+  if (!h || !out) return fail(B747_ERR_ARG, "null argument");
+  if (!h->trace.trk) return fail(B747_ERR_STATE, "handle was created without track_transfer");
+  CU(cudaSetDevice(h->cfg.device));
+  launch_transfer_metrics(h->dc, h->trace, which, finished, h->d_metrics, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, h->d_metrics, sizeof(double) * 5 * h->cfg.n_envs, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B747_OK;
+}
+static const char* kRecNames[NREC] = {"t", "U_com", "U_PID", "deltaz", "hzh", "vartheta_ref", "U_RL", "x", "y", "Vx", "Vy",
+                                      "vartheta", "wz"};
+extern "C" int b747_recorder_n_fields(void) { return NREC; }
+extern "C" const char* b747_recorder_field_name(int f) { return (f >= 0 && f < NREC) ? kRecNames[f] : nullptr; }
+extern "C" int b747_recorder_read(b747_handle* h, int env, double* out, int32_t* n_steps) {
+  if (!h || !out || !n_steps) return fail(B747_ERR_ARG, "null argument");
+  if (!h->trace.rec) return fail(B747_ERR_STATE, "handle was created with record_capacity = 0");
+  if (env < 0 || env >= h->cfg.n_envs) return fail(B747_ERR_ARG, "env out of range");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const int tick_field = b747_field_index("tick");
+  std::vector<double> ticks(h->cfg.n_envs);
+  int rc = b747_get_field(h, tick_field, ticks.data());
+  if (rc) return rc;
+  const int cap = h->trace.rec_cap, n = std::min(cap, (int)ticks[env]);
+  const size_t rs = (size_t)h->trace.rec_stride;
+  // rec[step][field][env]: one strided 2-D copy (one double per (step, field) row)
+  std::vector<double> tmp((size_t)cap * NREC);
+  CU(cudaMemcpy2D(tmp.data(), sizeof(double), h->trace.rec + env, sizeof(double) * rs, sizeof(double), (size_t)cap * NREC,
+                  cudaMemcpyDeviceToHost));
+  for (int f = 0; f < NREC; f++)
+    for (int k = 0; k < cap; k++) out[(size_t)f * cap + k] = k < n ? tmp[(size_t)k * NREC + f] : 0.0;
+  *n_steps = n;
+  return B747_OK;
+}
 extern "C" int b747_synchronize(b747_handle* h) {
   if (!h) return fail(B747_ERR_ARG, "null handle");
   CU(cudaStreamSynchronize(h->stream));

@@ -200,6 +200,84 @@ __device__ inline double nan_to_num(double x) {  // np.nan_to_num (core/model.py
   return x;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Trace: the reference's `Storage` recorder and `calc_stepinfo` (tools/general.py:46-61,315-329), hooked where
+// Controller._post_step records -- after EVERY model step (core/controller.py:209-228).
+//   recorder: rec[step][REC field][env] (float64), step = model step of the running episode (0-based), up to
+//             rec_cap steps; the recorded names and unit conversions are Controller._post_step's.
+//   tracker : calc_stepinfo evaluated online, O(1) state per env and signal -- first sample, extrema, last
+//             sample, index of the first sample inside the 5 % band (rise) and of the last one outside it
+//             (settling).  Slot 0 tracks the pitch angle against vartheta_ref (Controller.stepinfo_SS), slot 1
+//             the altitude against hzh (stepinfo_CS).  calc_stepinfo normalises every sample with the LAST
+//             reference value; the online form uses the current one, identical for the constant references
+//             the reference's evaluation harness uses (neural/callbacks.py:61-100, neural/agent.py:235-266).
+//   At `done` the tracker (+ Controller.quality) is copied to `snap` before the auto-reset clears it.
+// Evaluation feature: state sits in HBM and is read-modify-written per model step; a handle without it pays nothing.
+// ---------------------------------------------------------------------------------------------
+enum RecField { REC_t = 0, REC_U_com, REC_U_PID, REC_deltaz, REC_hzh, REC_vartheta_ref, REC_U_RL, REC_x, REC_y, REC_Vx,
+                REC_Vy, REC_vartheta, REC_wz, NREC };
+enum TrkField { TRK_y0 = 0, TRK_ymax, TRK_ymin, TRK_ylast, TRK_irise, TRK_iout, TRK_n, TRK_ybase, TRK_quality, NTRK };
+struct TraceState {
+  double* trk = nullptr;   // [2][NTRK][n_pad]
+  double* snap = nullptr;  // [2][NTRK][n_pad]
+  double* rec = nullptr;   // [rec_cap][NREC][rec_stride]
+  int rec_cap = 0;
+  int rec_stride = 0;      // = n_envs (no padding: a single-env facade records 2000 x 13 doubles, not x 128)
+};
+struct TraceSample {  // what Controller._post_step reads after one model step (stage-4 signals), SI units / radians
+  double t, U_com, U_PID, deltaz_RP, hzh, vref, U_RL, x, y, Vx, Vy, th, wz;
+};
+
+__device__ inline void trk_update(double* __restrict__ T, size_t np, int i, double y, double ybase) {
+#define TK(f) T[(size_t)(f) * np + i]
+  const double n = TK(TRK_n);
+  double y0 = TK(TRK_y0), ymax = TK(TRK_ymax), ymin = TK(TRK_ymin), irise = TK(TRK_irise), iout = TK(TRK_iout);
+  if (n == 0.0) { y0 = y; ymax = y; ymin = y; irise = -1.0; iout = -1.0; }
+  ymax = y > ymax ? y : ymax;
+  ymin = y < ymin ? y : ymin;
+  const double band = 0.05, ratio = (y - y0) / (ybase - y0);
+  if (irise < 0.0 && ratio >= (1 - band)) irise = n;
+  if (ratio <= 1 - band || ratio >= 1 + band) iout = n;
+  TK(TRK_y0) = y0; TK(TRK_ymax) = ymax; TK(TRK_ymin) = ymin; TK(TRK_ylast) = y; TK(TRK_irise) = irise;
+  TK(TRK_iout) = iout; TK(TRK_n) = n + 1.0; TK(TRK_ybase) = ybase;
+#undef TK
+}
+
+// after one model step; `step` = 0-based model step of the episode (tick after the step - 1)
+__device__ inline void trace_model_step(const TraceState& tr, size_t np, int i, int step, const TraceSample& s) {
+  const double vartheta_deg = nan_to_num(s.th) * (180 / kPi);  // `v *= 180/pi` on state_dict['vartheta']
+  const double vref_deg = s.vref * 180 / kPi;                  // self.vartheta_ref*180/pi
+  if (tr.rec && step < tr.rec_cap) {
+    const size_t rs = (size_t)tr.rec_stride;
+    double* R = tr.rec + ((size_t)step * NREC) * rs + i;
+    R[REC_t * rs] = s.t; R[REC_U_com * rs] = s.U_com; R[REC_U_PID * rs] = s.U_PID;
+    R[REC_deltaz * rs] = s.deltaz_RP * 180 / kPi; R[REC_hzh * rs] = s.hzh; R[REC_vartheta_ref * rs] = vref_deg;
+    R[REC_U_RL * rs] = s.U_RL; R[REC_x * rs] = nan_to_num(s.x); R[REC_y * rs] = nan_to_num(s.y);
+    R[REC_Vx * rs] = nan_to_num(s.Vx); R[REC_Vy * rs] = nan_to_num(s.Vy); R[REC_vartheta * rs] = vartheta_deg;
+    R[REC_wz * rs] = nan_to_num(s.wz);
+  }
+  if (tr.trk) {
+    trk_update(tr.trk, np, i, vartheta_deg, vref_deg);
+    trk_update(tr.trk + (size_t)NTRK * np, np, i, nan_to_num(s.y), s.hzh);
+  }
+}
+
+// at done: freeze the finished episode's tracker (+ Controller.quality, core/controller.py:334-336)
+__device__ inline void trace_snapshot(const TraceState& tr, size_t np, int i, double quality) {
+  if (!tr.trk) return;
+  for (int w = 0; w < 2; w++)
+    for (int f = 0; f < NTRK; f++) {
+      const size_t k = ((size_t)w * NTRK + f) * np + i;
+      tr.snap[k] = f == TRK_quality ? quality : tr.trk[k];
+    }
+}
+__device__ inline void trace_clear(const TraceState& tr, size_t np, int i) {
+  if (!tr.trk) return;
+  tr.trk[(size_t)TRK_n * np + i] = 0.0;
+  tr.trk[((size_t)NTRK + TRK_n) * np + i] = 0.0;
+}
+
 __host__ __device__ inline int obs_dim_of(int obs_type) {
   switch (obs_type) {
     case B747_OBS_PID_LIKE: return 3;

@@ -18,6 +18,7 @@ struct StateF64 {
   double* stats;     // [4] episodes, sum return, sum length, sum return^2
   double* last_ret;  // [n_pad] return of the most recently finished episode
   int* last_len;     // [n_pad] its length in env steps
+  TraceState trace;  // recorder / step-response tracker (optional)
 };
 
 // Device pointers of an f32 (throughput) handle; layout in b747_kernels_f32.cu.
@@ -28,6 +29,7 @@ struct StateF32 {
   double* stats = nullptr;
   double* last_ret = nullptr;
   int* last_len = nullptr;
+  TraceState trace;  // recorder / step-response tracker (optional; routes the launch to the general kernel)
   float4* tables = nullptr;  // merged-axis look-up tables (b747_tables.h), ft::CELLS float4
 };
 
@@ -49,5 +51,9 @@ void launch_reset64(const DevCfg& c, const StateF64& st, const uint8_t* mask, co
                     cudaStream_t s);
 void launch_defaults64(const DevCfg& c, const StateF64& st, cudaStream_t s);
 void launch_model_init64(const DevCfg& c, const StateF64& st, cudaStream_t s);
+// calc_stepinfo's final arithmetic on the tracker (snapshot != 0: the last finished episode): out[env][5] =
+// overshoot %, rise time, settling time, static error, Controller.quality (NaN where the reference returns None)
+void launch_transfer_metrics(const DevCfg& c, const TraceState& tr, int which, int snapshot, double* out_dev,
+                             cudaStream_t s);
 
 }  // namespace b747

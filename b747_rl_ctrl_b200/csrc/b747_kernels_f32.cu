@@ -191,9 +191,19 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
     }
     PassMx o;
     Stage4Mx s4;
-    const bool want_x = GEN && c.obs_type == B747_OBS_MODEL_STATE;
+    const bool tracing = GEN && (st.trace.trk || st.trace.rec);
+    const bool want_x = GEN && (c.obs_type == B747_OBS_MODEL_STATE || tracing);
 #pragma unroll 1
-    for (int k = 0; k < c.substeps; k++) model_step32<GEN>(sT, mp, c, r, o, s4, want_x);
+    for (int k = 0; k < c.substeps; k++) {
+      model_step32<GEN>(sT, mp, c, r, o, s4, want_x);
+      if (GEN && tracing) {  // Controller._post_step (core/controller.py:209-228)
+        TraceSample ts;
+        ts.t = (double)r.tick * kH; ts.U_com = o.U_com; ts.U_PID = o.U_com_PID; ts.deltaz_RP = o.deltaz_RP;
+        ts.hzh = r.href; ts.vref = use_ctrl ? (double)o.vartheta_zh : r.vartheta; ts.U_RL = a;
+        ts.x = s4.x; ts.y = s4.h; ts.Vx = s4.Vx; ts.Vy = s4.Vy; ts.th = o.thd; ts.wz = s4.wz;
+        trace_model_step(st.trace, np, i, r.tick - 1, ts);
+      }
+    }
     r.sig_upid = o.U_com_PID; r.sig_vzh = o.vartheta_zh;
     // stage-4 Derivative-block signals (float64 differences of the pitch error)
     const double dv_dt = (o.dv - r.d1_u) * 100.0;
@@ -231,6 +241,11 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
         if (c.norm_obs)
           for (int k = 0; k < n; k++) obs[k] /= mx[k];
       }
+    }
+    if (GEN && st.trace.trk) {  // Controller.quality of the running episode
+      const double q = exp(-60 * 0.1 * s4.itse / (c.tk * ((double)vr * (double)vr)));
+      st.trace.trk[(size_t)TRK_quality * np + i] = q;
+      st.trace.trk[((size_t)NTRK + TRK_quality) * np + i] = q;
     }
     // reward (env/ctrl_env.py:109-192)
     float rew = 0.f;
@@ -293,7 +308,9 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
     if (done) {
       ep_ret = r.ep_return; ep_len = (double)(r.tick / c.substeps);
       st.last_ret[i] = ep_ret; st.last_len[i] = r.tick / c.substeps;
+      if (GEN && st.trace.trk) trace_snapshot(st.trace, np, i, st.trace.trk[(size_t)TRK_quality * np + i]);
       if (c.auto_reset) {
+        if (GEN) trace_clear(st.trace, np, i);
         Episode ep;
         if (c.reset_ref_mode == B747_RESET_NONE) episode_from_state_mx(st, np, i, r, ep);
         else { draw_episode(c, (uint64_t)(c.env_id_offset + i), r.ep_idx, ep); r.ep_idx++; }
@@ -337,6 +354,7 @@ __global__ void __launch_bounds__(128) k_reset32(DevCfg c, StateF32 st, const ui
     r.ep_idx++;
   }
   env_reset_mx<GEN>(c, ep, r, st, np, i);
+  trace_clear(st.trace, np, i);
   if (obs_out)
     for (int k = 0; k < c.obs_dim; k++) obs_out[(size_t)i * c.obs_dim + k] = 0.f;
   if (st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
@@ -408,7 +426,7 @@ static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s) {
   const MP32 mp = make_mp32(c.mp);
-  if (f32_is_lean(c))
+  if (f32_is_lean(c) && !st.trace.trk && !st.trace.rec)
     k_env_step32<false><<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else
     k_env_step32<true><<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);

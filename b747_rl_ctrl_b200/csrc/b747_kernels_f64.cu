@@ -219,10 +219,26 @@ __global__ void __launch_bounds__(128) k_env_step64(DevCfg c, StateF64 st, const
       }
       r.deltaz = dz;
     }
+    const bool tracing = st.trace.trk || st.trace.rec;
 #pragma unroll 1
-    for (int k = 0; k < c.substeps; k++) model_step64(sP, c.mp, r, o, Xs4);
+    for (int k = 0; k < c.substeps; k++) {
+      model_step64(sP, c.mp, r, o, Xs4);
+      if (tracing) {  // Controller._post_step (core/controller.py:209-228)
+        TraceSample ts;
+        ts.t = (double)r.tick * kH; ts.U_com = o.U_com; ts.U_PID = o.U_com_PID; ts.deltaz_RP = o.deltaz_RP;
+        ts.hzh = r.h_zh; ts.vref = r.use_PID_CS != 0.0 ? o.vartheta_zh : r.vartheta; ts.U_RL = a;
+        ts.x = Xs4[IX_x]; ts.y = Xs4[IX_h]; ts.Vx = Xs4[IX_Vx]; ts.Vy = Xs4[IX_Vy]; ts.th = o.th; ts.wz = Xs4[IX_wz];
+        trace_model_step(st.trace, np, i, r.tick - 1, ts);
+      }
+    }
     r.sig_upid = o.U_com_PID; r.sig_vzh = o.vartheta_zh;
     const double time = (double)r.tick * kH;
+    if (st.trace.trk) {  // Controller.quality of the running episode
+      const double vr = vartheta_ref64(r);
+      const double q = exp(-60 * 0.1 * Xs4[IX_itse] / (c.tk * (vr * vr)));
+      st.trace.trk[(size_t)TRK_quality * np + i] = q;
+      st.trace.trk[((size_t)NTRK + TRK_quality) * np + i] = q;
+    }
     double obs[10];
     get_obs64(c, r, o, Xs4, obs);
     double rew = get_reward64(c, r, o, Xs4[IX_itse], time);
@@ -238,7 +254,9 @@ __global__ void __launch_bounds__(128) k_env_step64(DevCfg c, StateF64 st, const
     if (done) {
       ep_ret = r.ep_return; ep_len = (double)(r.tick / c.substeps);
       st.last_ret[i] = ep_ret; st.last_len[i] = r.tick / c.substeps;
+      if (st.trace.trk) trace_snapshot(st.trace, np, i, st.trace.trk[(size_t)TRK_quality * np + i]);
       if (c.auto_reset) {
+        trace_clear(st.trace, np, i);
         Episode ep;
         if (c.reset_ref_mode == B747_RESET_NONE) episode_from_slots(st.slots, np, i, r, ep);
         else { draw_episode(c, (uint64_t)(c.env_id_offset + i), r.ep_idx, ep); r.ep_idx++; }
@@ -296,6 +314,7 @@ __global__ void __launch_bounds__(128) k_reset64(DevCfg c, StateF64 st, const ui
     r.ep_idx++;
   }
   env_reset64(c, sP, ep, r, st.slots, np, i);
+  trace_clear(st.trace, np, i);
   if (obs_out)
     for (int k = 0; k < c.obs_dim; k++) obs_out[(size_t)i * c.obs_dim + k] = 0.0;
   if (st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.0;
@@ -342,7 +361,33 @@ __global__ void __launch_bounds__(128) k_model_init64(DevCfg c, StateF64 st) {
   store_regs64(st.slots, st.tick, st.flags, st.ep_idx, np, i, r);
 }
 
+// calc_stepinfo's final arithmetic (tools/general.py:46-61) + Controller.quality for every env.
+// ts[j] = fl((j+1)*0.01) is model.time after model step j, so ts[j]-ts[0] reproduces the reference's floats.
+__global__ void __launch_bounds__(128) k_transfer_metrics(int n_envs, size_t np, const double* __restrict__ T,
+                                                          double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_envs) return;
+#define TK(f) T[(size_t)(f) * np + i]
+  const double qnan = nan("");
+  const double n = TK(TRK_n), ybase = TK(TRK_ybase), irise = TK(TRK_irise), iout = TK(TRK_iout);
+  double* o = out + (size_t)i * 5;
+  if (!(n > 0.0)) { o[0] = o[1] = o[2] = o[3] = qnan; o[4] = TK(TRK_quality); return; }
+  const double t0 = 1.0 * kH;
+  o[0] = ybase != 0.0 ? ((ybase > 0.0 ? TK(TRK_ymax) : TK(TRK_ymin)) - ybase) / ybase * 100 : qnan;
+  o[1] = (irise >= 0.0 && irise <= n - 2.0) ? (irise + 1.0) * kH - t0 : qnan;  // range(0, len-1) skips the last sample
+  o[2] = iout >= 0.0 ? (iout + 1.0) * kH - t0 : qnan;
+  o[3] = fabs(TK(TRK_ylast) - ybase);
+  o[4] = TK(TRK_quality);
+#undef TK
+}
+
 static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
+
+void launch_transfer_metrics(const DevCfg& c, const TraceState& tr, int which, int snapshot, double* out_dev,
+                             cudaStream_t s) {
+  const double* T = (snapshot ? tr.snap : tr.trk) + (size_t)(which ? 1 : 0) * NTRK * (size_t)c.n_pad;
+  k_transfer_metrics<<<grid_for(c.n_envs, 128), 128, 0, s>>>(c.n_envs, (size_t)c.n_pad, T, out_dev);
+}
 
 void launch_env_step64(const DevCfg& c, const StateF64& st, const double* actions, double* obs, double* rew,
                        uint8_t* done, double* term_obs, cudaStream_t s) {

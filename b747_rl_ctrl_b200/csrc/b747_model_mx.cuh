@@ -81,6 +81,7 @@ struct RegsMx {
 
 struct PassMx {
   double dv;
+  double thd;  // folded pitch in float64 (trace only)
   float dvf;
   float th, V, alpha, Mach, CXa, CYa, mz, K_alpha, dCm, U_com, U_com_PID, deltaz_RP, vartheta_zh, td, rl_out;
   bool and_ss, and_cs;
@@ -181,6 +182,7 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
     cs = fmaf(z, pc, 1.0f);
   }
   o.th = thf;
+  o.thd = th_fold;
   const float ub = fmaf(cs, Vx, sn * Vy);
   const float wb = fmaf(cs, Vy, -sn * Vx);
   const float V2 = fmaf(ub, ub, wb * wb);

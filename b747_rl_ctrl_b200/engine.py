@@ -25,7 +25,7 @@ def make_cfg(n_envs, dtype=F32, device=0, obs_type=OBS_PID_LIKE, rew_type=REW_CL
              ctrl_mode=MODE_DIRECT, reset_ref_mode=RESET_CONST, disturbance_mode=DIST_NONE, norm_obs=True,
              norm_act=True, use_limiter=False, tk=20.0, sample_time=0.05, action_max=17 * math.pi / 180,
              vartheta_max=10 * math.pi / 180, reward_config=None, aero_err=None, seed=1, auto_reset=True,
-             env_layer=True, env_id_offset=0, export_signals=False):
+             env_layer=True, env_id_offset=0, export_signals=False, track_transfer=False, record_capacity=0):
     """Defaults are the canonical configuration main.py:88-121 trains."""
     c = Cfg()
     c.abi_version = _lib.ABI_VERSION
@@ -46,6 +46,8 @@ def make_cfg(n_envs, dtype=F32, device=0, obs_type=OBS_PID_LIKE, rew_type=REW_CL
         for i in range(5):
             c.fixed_aero_err[i] = float(aero_err[i])
     c.export_signals = int(bool(export_signals))
+    c.track_transfer = int(bool(track_transfer))
+    c.record_capacity = int(record_capacity)
     return c
 
 
@@ -192,6 +194,29 @@ class BatchEngine:
         v = np.zeros(n, np.float64)
         check(self._L.b747_get_param(self._h, name.encode(), v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n))
         return v if n > 1 else float(v[0])
+
+    # -- trace: step-response metrics and the Storage recorder -------------------------------------------------
+    METRIC_NAMES = ("overshoot", "rise_time", "settling_time", "static_error", "quality")
+
+    def transfer_metrics(self, which="SS", finished=True):
+        """calc_stepinfo (tools/general.py:46-61) + Controller.quality per env, computed in-kernel; [n_envs, 5] float64
+        in METRIC_NAMES order, NaN where the reference returns None.  which: "SS" pitch / "CS" altitude."""
+        out = np.empty((self.n_envs, 5), np.float64)
+        check(self._L.b747_transfer_metrics(self._h, 0 if which == "SS" else 1, int(bool(finished)), _ptr(out)))
+        return out
+
+    def recorder_fields(self):
+        return [self._L.b747_recorder_field_name(i).decode() for i in range(self._L.b747_recorder_n_fields())]
+
+    def recorder_read(self, env=0):
+        """The running episode of one env as {name: float64 array}, one entry per MODEL step (the reference's
+        Storage after Controller._post_step, core/controller.py:209-228)."""
+        names = self.recorder_fields()
+        cap = self.cfg.record_capacity
+        buf = np.zeros((len(names), max(cap, 1)), np.float64)
+        n = ctypes.c_int32(0)
+        check(self._L.b747_recorder_read(self._h, int(env), _ptr(buf), ctypes.byref(n)))
+        return {nm: buf[k, :n.value].copy() for k, nm in enumerate(names)}
 
     # -- episode statistics ---------------------------------------------------------------------
     def episode_stats(self):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B747_ABI_VERSION 1
+#define B747_ABI_VERSION 2
 
 /* Return codes */
 enum { B747_OK = 0, B747_ERR_ARG = -1, B747_ERR_CUDA = -2, B747_ERR_ALLOC = -3, B747_ERR_STATE = -4 };
@@ -68,6 +68,10 @@ typedef struct b747_cfg {
   double fixed_aero_err[5];
   int32_t has_fixed_aero_err;
   int32_t export_signals;  /* 1: every step also writes the DLL's exported signals (stage-4 values) per env */
+  int32_t track_transfer;  /* 1: calc_stepinfo (tools/general.py:46-61) evaluated online after every MODEL step, for the
+                              pitch angle vs vartheta_ref (Controller.stepinfo_SS) and the altitude vs hzh (stepinfo_CS) */
+  int32_t record_capacity; /* > 0: Controller(use_storage=True) -- record what Controller._post_step records
+                              (core/controller.py:209-228) for the first record_capacity model steps of the running episode */
 } b747_cfg;
 
 /* Per-episode initial condition and reference (what Controller.reset decides, core/controller.py:134-201). */
@@ -139,6 +143,18 @@ int b747_set_field(b747_handle *h, int field, const double *in_host);
 int b747_episode_stats(b747_handle *h, double out_host[4]);
 /* Per-env return/length of the most recently finished episode (VecMonitor's infos[i]["episode"]). */
 int b747_last_episode(b747_handle *h, double *ret_host, int32_t *len_host);
+
+/* Step-response metrics (handles created with track_transfer): out_host[n_envs][5] = overshoot [%], rise time [s],
+ * settling time [s], static error, Controller.quality() -- calc_stepinfo's definitions (5 % band, times relative to
+ * the first recorded sample); NaN where the reference returns None.  which: 0 = pitch (stepinfo_SS), 1 = altitude
+ * (stepinfo_CS).  finished: 0 = the running episode so far, 1 = the most recently finished episode. */
+int b747_transfer_metrics(b747_handle *h, int which, int finished, double *out_host);
+/* Recorder (handles created with record_capacity > 0): the running episode of one env, field-major:
+ * out_host[b747_recorder_n_fields()][record_capacity]; *n_steps = recorded model steps. Field names are the
+ * reference Storage's: t, U_com, U_PID, deltaz [deg], hzh, vartheta_ref [deg], U_RL, x, y, Vx, Vy, vartheta [deg], wz. */
+int b747_recorder_n_fields(void);
+const char *b747_recorder_field_name(int field);
+int b747_recorder_read(b747_handle *h, int env, double *out_host, int32_t *n_steps);
 
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 int64_t b747_launch_count(b747_handle *h);

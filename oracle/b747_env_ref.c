@@ -209,8 +209,33 @@ static double get_reward(b747o_env *e) {
   return 0.0;
 }
 
+/* Controller._post_step with use_storage, core/controller.py:209-228: names, order and unit conversions as there
+ * (`deltaz_real*180/pi`, `vartheta_ref*180/pi` multiply first; state_dict['vartheta'] is `v *= 180/pi`). */
+static void post_step(b747o_env *e, double action) {
+  if (!e->rec || e->rec_n >= e->rec_cap) return;
+  const b747o_iface *m = &e->mdl;
+  double *r = e->rec + (size_t)e->rec_n * B747O_NREC;
+  r[B747O_REC_t] = *m->sim_time;
+  r[B747O_REC_U_com] = *m->U_com;
+  r[B747O_REC_U_PID] = *m->U_com_PID;
+  r[B747O_REC_deltaz] = *m->deltaz_RP * 180 / M_PI;
+  r[B747O_REC_hzh] = *m->h_zh;
+  r[B747O_REC_vartheta_ref] = vartheta_ref(e) * 180 / M_PI;
+  r[B747O_REC_U_RL] = action;
+  r[B747O_REC_x] = nan_to_num(m->state[0]); r[B747O_REC_y] = nan_to_num(m->state[1]);
+  r[B747O_REC_Vx] = nan_to_num(m->state[2]); r[B747O_REC_Vy] = nan_to_num(m->state[3]);
+  r[B747O_REC_vartheta] = nan_to_num(m->state[4]) * (180 / M_PI);
+  r[B747O_REC_wz] = nan_to_num(m->state[5]);
+  e->rec_n++;
+}
+void b747o_env_set_recorder(b747o_env *e, double *buf, int32_t capacity_steps) {
+  e->rec = buf; e->rec_cap = capacity_steps; e->rec_n = 0;
+}
+int32_t b747o_env_recorded(const b747o_env *e) { return e->rec_n; }
+
 void b747o_env_reset_to(b747o_env *e, const b747o_episode *ep, double *obs) {
   b747o_iface *m = &e->mdl;
+  e->rec_n = 0;
   if (ep != &e->ep) e->ep = *ep;
   if (e->cfg.reset_ref_mode != B747_RESET_HYBRID)
     e->ep.use_ctrl = e->cfg.ctrl_type == B747_CTRL_SEMI_MANUAL || e->cfg.ctrl_type == B747_CTRL_FULL_AUTO;
@@ -261,7 +286,10 @@ int b747o_env_step(b747o_env *e, double action, double *obs, double *reward) {
     }
     *m->deltaz = dz;
   }
-  for (int k = 0; k < c->substeps; k++) m->step(m->ctx); /* K-loop, core/controller.py:255-264 */
+  for (int k = 0; k < c->substeps; k++) { /* K-loop, core/controller.py:255-264 */
+    m->step(m->ctx);
+    post_step(e, action);
+  }
   get_obs(e, obs);
   double r = get_reward(e);
   *reward = r;

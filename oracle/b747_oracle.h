@@ -119,7 +119,15 @@ typedef struct b747o_env {
   double ep_return;
   double tf_tp;            /* TF_REFERENCE closure state (env/ctrl_env.py:178) */
   int32_t obs_dim;
+  /* Controller(use_storage=True): what Controller._post_step records after every model step
+   * (core/controller.py:209-228), rec[step][B747O_NREC]; reset clears it (core/controller.py:195-199). */
+  double *rec;
+  int32_t rec_cap, rec_n;
 } b747o_env;
+enum { B747O_REC_t = 0, B747O_REC_U_com, B747O_REC_U_PID, B747O_REC_deltaz, B747O_REC_hzh, B747O_REC_vartheta_ref,
+       B747O_REC_U_RL, B747O_REC_x, B747O_REC_y, B747O_REC_Vx, B747O_REC_Vy, B747O_REC_vartheta, B747O_REC_wz, B747O_NREC };
+void b747o_env_set_recorder(b747o_env *e, double *buf, int32_t capacity_steps);
+int32_t b747o_env_recorded(const b747o_env *e);
 
 int b747o_obs_dim(int obs_type);
 int64_t b747o_done_tick(double tk);

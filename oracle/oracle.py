@@ -138,6 +138,56 @@ def build(force=False):
 _olib = None
 
 
+REC_FIELDS = ("t", "U_com", "U_PID", "deltaz", "hzh", "vartheta_ref", "U_RL", "x", "y", "Vx", "Vy", "vartheta", "wz")
+
+
+def stepinfo(ys, y_base, ts, error_band=0.05):
+    """Step-response figures of a recorded signal, as tools/general.py:46-61 defines them: overshoot in % of the
+    reference (peak on the reference's side), rise time = first sample (the last one excluded) whose normalised
+    response reaches 1 - band, settling time = LAST sample outside the +-band, both counted from the first
+    sample's time stamp; static error = |last - reference|.  None where the reference returns None."""
+    ys = [float(v) for v in ys]
+    n = len(ys)
+    norm = [(y - ys[0]) / (y_base - ys[0]) for y in ys]
+    peak = max(ys) if y_base > 0 else min(ys)
+    info = {"overshoot": (peak - y_base) / y_base * 100 if y_base != 0 else None, "rise_time": None,
+            "settling_time": None, "static_error": abs(ys[-1] - y_base)}
+    for i in range(n - 1):
+        if norm[i] >= 1 - error_band:
+            info["rise_time"] = ts[i] - ts[0]
+            break
+    for i in range(n - 1, -1, -1):
+        if norm[i] <= 1 - error_band or norm[i] >= 1 + error_band:
+            info["settling_time"] = ts[i] - ts[0]
+            break
+    return info
+
+
+class _Recorder:
+    """Mixin: Controller(use_storage=True) for one oracle env (pointer in self._e)."""
+
+    def enable_storage(self, capacity):
+        L = self._L
+        L.b747o_env_set_recorder.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+        L.b747o_env_recorded.restype = ctypes.c_int32
+        L.b747o_env_recorded.argtypes = [ctypes.c_void_p]
+        self._rec = np.zeros((int(capacity), len(REC_FIELDS)))
+        L.b747o_env_set_recorder(self._e, _dptr(self._rec), int(capacity))
+
+    @property
+    def storage(self):
+        n = self._L.b747o_env_recorded(self._e)
+        return {nm: self._rec[:n, k].copy() for k, nm in enumerate(REC_FIELDS)}
+
+    def stepinfo_SS(self):
+        st = self.storage
+        return stepinfo(st["vartheta"], st["vartheta_ref"][-1], st["t"])
+
+    def stepinfo_CS(self):
+        st = self.storage
+        return stepinfo(st["y"], st["hzh"][-1], st["t"])
+
+
 def _proto_env_api(L):
     L.b747o_env_step.restype = ctypes.c_int
     L.b747o_env_step.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
@@ -274,6 +324,12 @@ class OracleBatch:
     def model(self, i):
         return CModel(self._L.b747o_batch_model(self._h, i))
 
+    def env(self, i):
+        """Recorder view of env i (enable_storage / storage / stepinfo_SS / stepinfo_CS)."""
+        v = _Recorder()
+        v._L, v._e = self._L, self._L.b747o_batch_env(self._h, i)
+        return v
+
 
 _rlib = None
 
@@ -294,7 +350,7 @@ def rlib():
     return _rlib
 
 
-class RefEnv:
+class RefEnv(_Recorder):
     """ControllerEnv equivalent driving a private instance of the reference DLL."""
 
     def __init__(self, cfg, env_id=0):

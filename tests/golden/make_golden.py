@@ -7,6 +7,8 @@ Run in the build container where /root/reference is mounted:
 Outputs (committed; they travel to the GPU box where the reference does not exist):
     model_kats.json   model-level known answers K1-K5: parameters, elevator stream,
                       final `state`, and all exported signals at a few step counts
+    transfer_golden.json  K6: the four PID transfer episodes of the reference's control test (ADD_PROC, a = 0, refs
+                      +-5, +-10 deg): calc_stepinfo figures, Controller.quality and every 50th Storage record
     env_golden.npz    env-level trajectories: for each named case the config, per-env episode
                       descriptors, action streams and the (obs, reward, done) the DLL-backed
                       ControllerEnv equivalent produced
@@ -121,11 +123,28 @@ def k7():
             "k7zero/obs": o0, "k7zero/rew": r0, "k7addproc/rew": r2}
 
 
+def transfer_golden():
+    """SURVEY.md 8c K6 / BASELINE.md: overshoot 9.263 %, settling 11.300 s, quality 0.7527 (means over the refs)."""
+    out = {}
+    for deg in (5, -5, 10, -10):
+        cfg = O.make_cfg(reset_ref_mode=O.RESET_NONE, ctrl_mode=O.MODE_ADD_PROC, action_max=1.0, rew_type=O.REW_QUALITY)
+        env = O.RefEnv(cfg)
+        env.enable_storage(2000)
+        env.reset_to(O.episode([0, 11000, 250, 0, 0, 0], vref=deg * DEG))
+        _, rew, done = env.rollout(np.zeros(400), auto_reset=False)
+        st = env.storage
+        out[str(deg)] = dict(stepinfo=env.stepinfo_SS(), stepinfo_CS=env.stepinfo_CS(), quality=float(rew[-1]),
+                             n=len(st["t"]), samples={k: [float(x) for x in v[49::50]] for k, v in st.items()})
+    return out
+
+
 if __name__ == "__main__":
     if not dllref.available():
         sys.exit("oracle/_ref/libb747_ref.so missing: run `make -C oracle ref` where /root/reference is mounted")
     with open(os.path.join(HERE, "model_kats.json"), "w") as f:
         json.dump(model_kats(), f, indent=0)
+    with open(os.path.join(HERE, "transfer_golden.json"), "w") as f:
+        json.dump(transfer_golden(), f, indent=0)
     g = env_golden()
     g.update(k7())
     np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **g)
