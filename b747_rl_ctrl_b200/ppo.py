@@ -1,0 +1,171 @@
+"""End-to-end PPO on the GPU environment (BASELINE.json configs[4]: 65536-env GPU VecEnv, torch MLP policy).
+
+The reference trains `PPO('MlpPolicy', env)` from stable-baselines3 1.4.0 with default hyper-parameters on
+`SubprocVecEnv([env] * 4)` (neural/agent.py:46-81; setups.py's dict never matches, so the defaults apply): 2 x 64 tanh
+MLPs for policy and value, state-independent log-std, Adam(3e-4, eps 1e-5), gamma 0.99, GAE lambda 0.95, clip 0.2,
+vf_coef 0.5, max_grad_norm 0.5, advantage normalisation, 10 epochs.  stable-baselines3 is not installed in this image,
+so the algorithm is restated here in plain torch with those defaults; what changes with 65536 environments is the
+rollout geometry only (n_steps x n_envs samples per update and the minibatch size), which are arguments.
+
+Observations, actions, rewards and dones never leave HBM: the environment step is one launch of k_env_step32 on
+torch's current stream, the policy is a torch module on the same device.  Episodes end by the time limit and are
+treated as terminal, as SB3 does for an env that sets no `TimeLimit.truncated` (the reference's info dict is empty).
+
+    python -m b747_rl_ctrl_b200.ppo --envs 65536 --threshold 225
+prints one JSON line: env-steps/s (rollout + update, like SB3's time/fps) and wall-clock to the reward threshold
+(the reference run reached ep_rew_mean 225.7 after 98 304 steps at ~340 steps/s).
+"""
+import argparse
+import json
+import math
+import time
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+
+
+class ActorCritic(nn.Module):
+    """SB3 MlpPolicy defaults: separate 2 x 64 tanh networks, orthogonal init (gain sqrt2 / 0.01 / 1), log_std = 0."""
+
+    def __init__(self, obs_dim, hidden=64):
+        super().__init__()
+        def mlp(out_gain):
+            layers = [nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(), nn.Linear(hidden, 1)]
+            for m in layers[:-1]:
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, math.sqrt(2)); nn.init.zeros_(m.bias)
+            nn.init.orthogonal_(layers[-1].weight, out_gain); nn.init.zeros_(layers[-1].bias)
+            return nn.Sequential(*layers)
+        self.pi = mlp(0.01)
+        self.vf = mlp(1.0)
+        self.log_std = nn.Parameter(torch.zeros(1))
+
+    def dist(self, obs):
+        return torch.distributions.Normal(self.pi(obs).squeeze(-1), self.log_std.exp())
+
+    def value(self, obs):
+        return self.vf(obs).squeeze(-1)
+
+
+def train(n_envs=65536, total_steps=None, threshold=225.0, max_seconds=600.0, n_steps=32, n_minibatches=16, n_epochs=4,
+          lr=3e-4, gamma=0.99, gae_lambda=0.95, clip=0.2, vf_coef=0.5, ent_coef=0.0, max_grad_norm=0.5, seed=1, device=0,
+          env_kwargs=None, log=None, desync=True):
+    torch.manual_seed(seed)
+    dev = torch.device("cuda", device)
+    torch.cuda.set_device(dev)
+    kw = dict(sample_time=0.05, tk=20.0)  # main.py:18, 95-96: K = 5, 400-step episodes
+    kw.update(env_kwargs or {})
+    eng = E.BatchEngine(n_envs=n_envs, dtype=E.F32, device=device, seed=seed, auto_reset=True, **kw)
+    eng.use_stream(torch.cuda.current_stream().cuda_stream)
+    act, obs, rew, done = eng.alloc_io()
+    eng.reset(obs)
+    od = eng.obs_dim
+    # Spread the episode phases: a VecEnv whose environments all start together keeps them in lock-step (every
+    # episode lasts exactly tk / sample_time steps), so each rollout would see a single slice of the episode.
+    ep_len = int(round(kw["tk"] / (kw["sample_time"] or 0.01)))
+    if desync and ep_len > 1:
+        ids = torch.arange(n_envs, device=dev)
+        act.zero_()
+        for t in range(ep_len):
+            eng.step(act, obs, rew, done)
+            mask = ((ids % ep_len) == t).to(torch.uint8)
+            eng.reset(mask=mask)
+        eng.step(act, obs, rew, done)
+        eng.episode_stats()  # discard the warm-up episodes
+    net = ActorCritic(od).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-5)
+    T, N = n_steps, n_envs
+    b_obs = torch.empty(T, N, od, device=dev); b_act = torch.empty(T, N, device=dev); b_logp = torch.empty(T, N, device=dev)
+    b_val = torch.empty(T, N, device=dev); b_rew = torch.empty(T, N, device=dev); b_done = torch.empty(T, N, device=dev)
+    mb = T * N // n_minibatches
+    steps_done, updates = 0, 0
+    history = []
+    t_hit = None
+    ep_n = ep_sum = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    while True:
+        with torch.no_grad():
+            for t in range(T):
+                d = net.dist(obs)
+                a = d.sample()
+                b_obs[t] = obs; b_act[t] = a; b_logp[t] = d.log_prob(a); b_val[t] = net.value(obs)
+                torch.clamp(a, -1.0, 1.0, out=act)   # SB3 clips the action to the Box before env.step
+                eng.step(act, obs, rew, done)        # one kernel launch; obs is the reset observation where done
+                b_rew[t] = rew; b_done[t] = done
+            last_val = net.value(obs)
+            adv = torch.empty_like(b_rew)
+            gae = torch.zeros(N, device=dev)
+            for t in reversed(range(T)):
+                nonterm = 1.0 - b_done[t]
+                nxt = last_val if t == T - 1 else b_val[t + 1]
+                delta = b_rew[t] + gamma * nxt * nonterm - b_val[t]
+                gae = delta + gamma * gae_lambda * nonterm * gae
+                adv[t] = gae
+            ret = adv + b_val
+        f_obs, f_act, f_logp = b_obs.view(-1, od), b_act.view(-1), b_logp.view(-1)
+        f_adv, f_ret = adv.view(-1), ret.view(-1)
+        for _ in range(n_epochs):
+            perm = torch.randperm(T * N, device=dev)
+            for k in range(n_minibatches):
+                idx = perm[k * mb:(k + 1) * mb]
+                d = net.dist(f_obs[idx])
+                logp = d.log_prob(f_act[idx])
+                a_mb = f_adv[idx]
+                a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
+                ratio = (logp - f_logp[idx]).exp()
+                pg = -torch.min(ratio * a_mb, ratio.clamp(1 - clip, 1 + clip) * a_mb).mean()
+                v_loss = ((net.value(f_obs[idx]) - f_ret[idx]) ** 2).mean()
+                loss = pg + vf_coef * v_loss - ent_coef * d.entropy().mean()
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(net.parameters(), max_grad_norm)
+                opt.step()
+        steps_done += T * N
+        updates += 1
+        st = eng.episode_stats()  # in-kernel episode statistics since the last call (the only host read per update)
+        now = time.perf_counter() - t0
+        if st[0] > 0:
+            ep_n, ep_sum = st[0], st[1]
+            mean_r = ep_sum / ep_n
+            history.append((steps_done, now, mean_r))
+            if log:
+                log(f"update {updates:4d}  steps {steps_done:.3e}  {steps_done / now:.3e} steps/s  ep_rew_mean {mean_r:8.2f}")
+            if t_hit is None and threshold is not None and mean_r >= threshold:
+                t_hit = (now, steps_done, mean_r)
+                break
+        if (total_steps and steps_done >= total_steps) or now > max_seconds:
+            break
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    eng.close()
+    return dict(steps=steps_done, seconds=wall, steps_per_s=steps_done / wall, updates=updates, history=history,
+                threshold=threshold, reached=(None if t_hit is None else dict(seconds=t_hit[0], steps=t_hit[1], ep_rew_mean=t_hit[2])),
+                final_ep_rew_mean=(history[-1][2] if history else None), net=net)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--threshold", type=float, default=225.0)
+    ap.add_argument("--max-seconds", type=float, default=300.0)
+    ap.add_argument("--n-steps", type=int, default=32)
+    ap.add_argument("--minibatches", type=int, default=16)
+    ap.add_argument("--epochs", type=int, default=4)
+    ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--quiet", action="store_true")
+    a = ap.parse_args()
+    r = train(n_envs=a.envs, threshold=a.threshold, max_seconds=a.max_seconds, n_steps=a.n_steps, n_minibatches=a.minibatches,
+              n_epochs=a.epochs, lr=a.lr, log=None if a.quiet else print)
+    r.pop("net"); hist = r.pop("history")
+    r["history_tail"] = hist[-5:]
+    r["config"] = dict(envs=a.envs, n_steps=a.n_steps, minibatches=a.minibatches, epochs=a.epochs, lr=a.lr,
+                       env="PID_LIKE obs, CLASSIC reward, MANUAL/DIRECT_CONTROL, CONST reference, K=5, tk=20 (main.py:88-121)",
+                       policy="2x64 tanh MLP actor + critic (SB3 MlpPolicy defaults)")
+    print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
