@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
         r.vartheta = r.vref;
       }
     }
-    if (!(mp.use_PID_SS != 0.f)) {
+    if (!(mp.sw & SW_SS_ON)) {
       const float lim = (float)(17 * kPi / 180);
       float dz;
       switch (c.ctrl_mode) {
@@ -389,10 +389,11 @@ bool f32_is_lean(const DevCfg& c) {
 static MP32 make_mp32(const ModelParams& m) {
   MP32 p;
   for (int k = 0; k < 4; k++) p.PID_SS[k] = (float)m.PID_SS[k];
-  p.P = (float)m.P; p.g = (float)m.g; p.inv_m0 = (float)(1.0 / m.m0);
-  p.half_S = (float)(Pc(134) * m.S);
+  p.P_m = (float)(m.P / m.m0); p.g = (float)m.g;
+  p.kS_m = (float)(Pc(134) * m.S / m.m0);
   p.half_Sc_over_Iz = (float)(Pc(135) * m.S * m.c_ / m.Iz);
-  p.use_RP = (float)m.use_RP; p.use_RL = (float)m.use_RL; p.use_PID_SS = (float)m.use_PID_SS;
+  p.sw = (m.use_RL >= Pc(148) ? SW_RL : 0) | (m.use_PID_SS >= Pc(9) ? SW_SS : 0) | (m.use_RP >= Pc(149) ? SW_RP : 0) |
+         (m.use_PID_SS != 0.0 ? SW_SS_ON : 0);
   return p;
 }
 

@@ -60,9 +60,12 @@ __host__ __device__ constexpr int axis_off(int a) { return a == AX_M ? ft::AXM :
 constexpr int kFastCells = ft::CELLS;
 
 // float copies of the uniform tunables + folded constants (built on the host, b747_kernels_f32.cu)
+// Manual switches of the diagram, resolved on the host against their thresholds (P148, P9, P149)
+enum { SW_RL = 1, SW_SS = 2, SW_RP = 4, SW_SS_ON = 8 };
 struct MP32 {
   float PID_SS[4];
-  float P, g, inv_m0, half_S, half_Sc_over_Iz, use_RP, use_RL, use_PID_SS;
+  float P_m, g, kS_m, half_Sc_over_Iz;  // thrust / m0, g, P134 S / m0, P135 S c / Iz
+  int sw;
 };
 
 struct RegsMx {
@@ -112,16 +115,16 @@ __device__ __forceinline__ int sgnf(float x) { return (x > 0.f) - (x < 0.f); }
 // ---- rare paths, kept out of line so that the pass loop stays small in the instruction cache ----
 __device__ __noinline__ float atan2_far(float y, float x) { return atan2f(y, x); }
 
-// alpha = -atan2(wb, ub)
+// alpha = -atan2(wb, ub) = atan(-wb/ub) for ub > 0
 __device__ __forceinline__ float alpha_of(float wb, float ub) {
-  const float q = wb * rcp_fast(ub);
+  const float q = -wb * rcp_fast(ub);
   if (ub > 0.f && fabsf(q) <= poly::ATAN_MAX) {
     const float z = q * q;
     float p = fmaf(poly::ATAN6, z, poly::ATAN5); p = fmaf(p, z, poly::ATAN4); p = fmaf(p, z, poly::ATAN3);
     p = fmaf(p, z, poly::ATAN2); p = fmaf(p, z, poly::ATAN1); p = fmaf(p, z, poly::ATAN0);
-    return -fmaf(q * z, p, q);
+    return fmaf(q * z, p, q);
   }
-  return -atan2_far(wb, ub);
+  return atan2_far(-wb, ub);
 }
 
 // One axis: validate the cached interval (two compares), re-search incrementally if the operand left
@@ -150,30 +153,49 @@ __device__ __forceinline__ float bilinear(const float4 c, float f0, float f1) {
   return fmaf(yR - yL, f1, yL);
 }
 
+// Atmosphere of one model step: evaluated in full at the major pass, carried to the three minor passes by its first
+// derivative in h.  Within a step the altitude moves by |Vy| h < 1 m against a density scale height of ~8 km, so the
+// neglected second-order term is ~1e-9 relative (float32 rounds at 6e-8); only the step that crosses the ISA kinks
+// (0 m, 11 km) sees a one-off slope error of ~1e-5 relative, on a force that acts for 10 ms.
+struct AtmoMx { float h0, rho0, ia0, s_rho, s_ia; };
+
 // One pass over the diagram at a stage state.  stage: 0 major, 1/2 half steps, 3 full step.
+// Passes 0 and 3 -- the ones whose pitch error is differenced by the Derivative blocks, observed and rewarded -- carry
+// the pitch angle and the pitch error in float64 (th_d); the half-step passes only feed float32 RK4 sums and use th_f.
 template <bool GEN>
 __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, int stage, int n,
-                                       double th_d, float t_f, float h, double h_d, float Vx, float Vy, float wz,
-                                       float ssi, float ssf, double csi, double csf, RegsMx& r, bool& memout_ss,
-                                       bool& memout_cs, PassMx& o, float& f_h, float& f_Vx, float& f_Vy, float& f_wz,
-                                       float& f_ssi, float& f_ssf, double& f_csi, double& f_csf, float& f_itse) {
+                                       double th_d, float th_f, float vref_f, float t_f, float h, double h_d, float Vx,
+                                       float Vy, float wz, float ssi, float ssf, double csi, double csf, RegsMx& r,
+                                       AtmoMx& at, bool& memout_ss, bool& memout_cs, PassMx& o, float& f_h, float& f_Vx,
+                                       float& f_Vy, float& f_wz, float& f_ssi, float& f_ssf, double& f_csi, double& f_csf,
+                                       float& f_itse) {
   const bool major = stage == 0;
-  // attitude: polynomial sin/cos for |theta| <= pi/2; beyond that (libm sincos and the DLL's
-  // principal-value fold asin(sin(theta))) sits behind one rare branch
-  float thf = __double2float_rn(th_d);
-  float sn, cs;
+  const bool dbl = stage == 0 || stage == 3;
+  // attitude.  Beyond +-90 deg the DLL's pitch asin(sin(theta)) folds back: with k = round(theta/pi) and
+  // r = theta - k*pi (two-constant Cody-Waite reduction) asin(sin(theta)) = (-1)^k r, and the DLL's sin/cos of the
+  // folded pitch are sin(theta) and |cos(theta)| = cos(r).  Rare, cheap, and the polynomial covers the folded range.
+  float thf;
   double th_fold = th_d;
   static_assert(poly::SINCOS_MAX >= 1.57079632679f, "sin/cos polynomial must cover the unfolded pitch range");
-  if (fabsf(thf) > 1.57079632679f) {
-    // rare: beyond +-90 deg the DLL's pitch asin(sin(theta)) folds back.  With k = round(theta/pi) and
-    // r = theta - k*pi (two-constant Cody-Waite reduction in float64): asin(sin(theta)) = (-1)^k r, and the
-    // DLL's sin/cos of that folded pitch are sin(theta) and |cos(theta)| = cos(r).
-    const double k = rint(th_d * 0.318309886183790671538);
-    double rr = fma(-k, 3.141592653589793116, th_d);
-    rr = fma(-k, 1.2246467991473532e-16, rr);
-    th_fold = (((int)k) & 1) ? -rr : rr;
-    thf = __double2float_rn(th_fold);
+  if (dbl) {
+    thf = __double2float_rn(th_d);
+    if (fabsf(thf) > 1.57079632679f) {
+      const double k = rint(th_d * 0.318309886183790671538);
+      double rr = fma(-k, 3.141592653589793116, th_d);
+      rr = fma(-k, 1.2246467991473532e-16, rr);
+      th_fold = (((int)k) & 1) ? -rr : rr;
+      thf = __double2float_rn(th_fold);
+    }
+  } else {
+    thf = th_f;
+    if (fabsf(thf) > 1.57079632679f) {
+      const float k = rintf(thf * 0.318309886f);
+      float rr = fmaf(-k, 3.14159274f, thf);
+      rr = fmaf(-k, -8.74227766e-8f, rr);
+      thf = (((int)k) & 1) ? -rr : rr;
+    }
   }
+  float sn, cs;
   {
     const float z = thf * thf;
     float ps = fmaf(poly::SIN4, z, poly::SIN3); ps = fmaf(ps, z, poly::SIN2); ps = fmaf(ps, z, poly::SIN1); ps = fmaf(ps, z, poly::SIN0);
@@ -189,26 +211,49 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   const float rV = rsqrt_fast(V2);
   const float V = V2 * rV;
   const float alpha = alpha_of(wb, ub);
-  const float sa = -wb * rV, ca = ub * rV;
   o.V = V; o.alpha = alpha;
-  // ISA atmosphere
-  const float hs = fminf(fmaxf(h, PCF(18)), PCF(17));
-  const float T = fmaf(-hs, PCF(19), PCF(16));
-  const float Mach = V * rsqrt_fast(T * PCF(20));
-  const float ad = alpha * PCF(21);
+  // ISA atmosphere: density rho0 (T/T0)^(g/(LR)-1) [* exp(g/R sat(11000-h)/T) above the tropopause] and 1/a
+  float rho, ia;
+  if (major) {
+    const float hs = fminf(fmaxf(h, PCF(18)), PCF(17));
+    const float T = fmaf(-hs, PCF(19), PCF(16));
+    const float rT = rcp_fast(T);
+    ia = rsqrt_fast(T * PCF(20));
+    const float u = fmaf(T, PCF(127), -poly::RHO_CENTER);
+    float pr = fmaf(poly::RHO6, u, poly::RHO5); pr = fmaf(pr, u, poly::RHO4); pr = fmaf(pr, u, poly::RHO3);
+    pr = fmaf(pr, u, poly::RHO2); pr = fmaf(pr, u, poly::RHO1); pr = fmaf(pr, u, poly::RHO0);
+    const float dh = PCF(130) - h;
+    // the saturation makes the exponential exactly 1 below the tropopause: evaluated unconditionally (a third of the
+    // environments start within 3 km of 11 km, a branch would diverge in most warps)
+    rho = PCF(129) * pr * ex2_fast(fminf(fmaxf(dh, PCF(132)), PCF(131)) * (PCF(133) * 1.4426950408889634f) * rT);
+    // d/dh: troposphere (T not clamped): rho' = -rho (g/(LR)-1) L / T, (1/a)' = (1/a) L / (2T);
+    //       stratosphere (exponent not clamped): rho' = -rho (g/R) / T
+    const bool tropo = (h > PCF(18)) & (h < PCF(17));
+    const bool strato = (dh < PCF(131)) & (dh > PCF(132));
+    const float kr = (tropo ? (PCF(128) - 1.0f) * PCF(19) : 0.f) + (strato ? PCF(133) : 0.f);
+    at.h0 = h; at.rho0 = rho; at.ia0 = ia;
+    at.s_rho = -rho * rT * kr;
+    at.s_ia = tropo ? ia * rT * (0.5f * PCF(19)) : 0.f;
+  } else {
+    const float dlt = h - at.h0;
+    rho = fmaf(at.s_rho, dlt, at.rho0);
+    ia = fmaf(at.s_ia, dlt, at.ia0);
+  }
+  const float Mach = V * ia;
   o.Mach = Mach;
   // look-ups on the merged axes (b747_tables.h): one cached interval per operand.  Fast path: three
   // LDS.128 fetch the cached interval records, one combined predicate validates them; the incremental
   // re-search of an operand that left its interval is rare (Mach, alpha, h move ~1e-4 of an interval per pass).
+  // The alpha axis is stored in radians (breakpoints / P21), so no conversion to degrees is needed.
   float4 qM = axis_peek<AX_M>(sT, r.ax[AX_M]);
   float4 qA = axis_peek<AX_A>(sT, r.ax[AX_A]);
   float4 qH = axis_peek<AX_H>(sT, r.ax[AX_H]);
-  if (axis_miss(Mach, qM) | axis_miss(ad, qA) | axis_miss(h, qH)) {
+  if (axis_miss(Mach, qM) | axis_miss(alpha, qA) | axis_miss(h, qH)) {
     qM = axis_lookup<AX_M>(sT, Mach, r.ax[AX_M]);
-    qA = axis_lookup<AX_A>(sT, ad, r.ax[AX_A]);
+    qA = axis_lookup<AX_A>(sT, alpha, r.ax[AX_A]);
     qH = axis_lookup<AX_H>(sT, h, r.ax[AX_H]);
   }
-  const float fM = (Mach - qM.z) * qM.w, fA = (ad - qA.z) * qA.w, fH = (h - qH.z) * qH.w;
+  const float fM = (Mach - qM.z) * qM.w, fA = (alpha - qA.z) * qA.w, fH = (h - qH.z) * qH.w;
   const char* sB = (const char*)sT;
   // CYa and mz share the (Mach, alpha) cell: two adjacent 128-bit loads
   const float4* cMA = (const float4*)(sB + ft::T_MA * 16 + (r.ax[AX_A] * ft::NM + r.ax[AX_M]) * 2);
@@ -224,22 +269,14 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   float Ka = fmaf(kc.y, fA, kc.x);
   if (GEN) { dCm *= r.sumA[3]; Ka *= r.sumA[4]; mz *= r.sumA[2]; }
   o.dCm = dCm; o.K_alpha = Ka; o.mz = mz;
-  // density: rho0 * (T/T0)^(g/(LR)-1) [* exp(g/R * sat(11000-h) / T) above the tropopause]
-  const float u = fmaf(T, PCF(127), -poly::RHO_CENTER);
-  float pr = fmaf(poly::RHO6, u, poly::RHO5); pr = fmaf(pr, u, poly::RHO4); pr = fmaf(pr, u, poly::RHO3);
-  pr = fmaf(pr, u, poly::RHO2); pr = fmaf(pr, u, poly::RHO1); pr = fmaf(pr, u, poly::RHO0);
-  float rho = PCF(129) * pr;
-  const float dh = PCF(130) - h;
-  // exp(g/R * sat(11000-h) / T): the saturation makes the factor exactly 1 below the tropopause, so it is
-  // evaluated unconditionally (2 MUFU + 4 FP32 ops) instead of behind a divergent branch -- a third of the
-  // environments start within 3 km of 11 km
-  rho *= ex2_fast(fminf(fmaxf(dh, PCF(132)), PCF(131)) * (PCF(133) * 1.4426950408889634f) * rcp_fast(T));
+  // aerodynamic + thrust acceleration in body axes, straight from the body velocity components:
+  // drag/lift rotated by alpha with sin(alpha) = -wb/V, cos(alpha) = ub/V gives
+  //   Fx = q S (c_x ub - CYa wb)/V + P,  Fy = q S (CYa ub + c_x wb)/V,  q S / V = rho V S / 2,  c_x = P126 CXa
   const float rV2 = rho * V2;
-  const float qS = rV2 * mp.half_S;
-  const float mD = PCF(126) * CXa * qS;
-  const float Lf = qS * CYa;
-  const float Fx = fmaf(mD, ca, fmaf(sa, Lf, mp.P));
-  const float Fy = fmaf(ca, Lf, -mD * sa);
+  const float kq = rV2 * (rV * mp.kS_m);
+  const float cx = PCF(126) * CXa;
+  const float Fx = fmaf(kq, fmaf(-CYa, wb, cx * ub), mp.P_m);
+  const float Fy = kq * fmaf(cx, wb, CYa * ub);
   // actuator: transport delay (3 steps) -> discrete filter (every 5th tick) -> rate limiter -> saturation
   float td;
   if (stage == 0) td = n > 3 ? r.uh[1] : PCF(137);
@@ -257,10 +294,10 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   // СУ PID (altitude loop) -- only integrated when the configuration can close it.  Its output is the
   // pitch reference, which the СС PID differentiates with a gain of Kd*N ~ 390, so the whole
   // altitude-error chain is float64 (a float32 altitude quantises it at ~1e-5 rad).
-  float use_cs = 0.f;
+  bool use_cs = false;
   double cs_pre = 0.0, cs_d = 0.0, e_h = 0.0, vzh_d = 0.0;
   if (GEN) {
-    use_cs = (r.flags & FL_USE_CTRL) ? 1.f : 0.f;
+    use_cs = (r.flags & FL_USE_CTRL) && (1.f >= PCF(146));
     e_h = r.href - h_d;  // h_zh - h
     cs_d = (e_h * c.mp.PID_CS[2] - csf) * c.mp.PID_CS[3];
     cs_pre = e_h * c.mp.PID_CS[0] + csi + cs_d;
@@ -269,21 +306,25 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   } else {
     o.vartheta_zh = 0.f;
   }
-  // pitch error in float64
-  const double vref_d = (GEN && use_cs >= PCF(146)) ? vzh_d : r.vartheta;
-  const double dv_d = vref_d - th_fold;
-  o.dv = dv_d;
-  const float dv = __double2float_rn(dv_d);
+  // pitch error
+  float dv;
+  if (dbl) {
+    const double dv_d = ((GEN && use_cs) ? vzh_d : r.vartheta) - th_fold;
+    o.dv = dv_d;
+    dv = __double2float_rn(dv_d);
+  } else {
+    dv = ((GEN && use_cs) ? o.vartheta_zh : vref_f) - thf;
+  }
   o.dvf = dv;
   // СС PID
   const float ss_d = (dv * mp.PID_SS[2] - ssf) * mp.PID_SS[3];
   const float ss_pre = fmaf(dv, mp.PID_SS[0], ssi) + ss_d;
   o.U_com_PID = satf(ss_pre, PCF(5), PCF(7));
-  if (mp.use_RL >= PCF(148)) o.U_com = PCF(147) > fabsf(o.U_com_PID) ? 0.f : o.U_com_PID;
-  else o.U_com = mp.use_PID_SS >= PCF(9) ? o.U_com_PID : r.deltaz;
-  const float ax = (Fx * cs - sn * Fy) * mp.inv_m0;
-  const float ay = fmaf(fmaf(Fy, cs, Fx * sn), mp.inv_m0, -mp.g);
-  const float dze = mp.use_RP >= PCF(149) ? o.deltaz_RP : o.U_com;
+  if (mp.sw & SW_RL) o.U_com = PCF(147) > fabsf(o.U_com_PID) ? 0.f : o.U_com_PID;
+  else o.U_com = (mp.sw & SW_SS) ? o.U_com_PID : r.deltaz;
+  const float ax = fmaf(Fx, cs, -sn * Fy);
+  const float ay = fmaf(Fy, cs, fmaf(Fx, sn, -mp.g));
+  const float dze = (mp.sw & SW_RP) ? o.deltaz_RP : o.U_com;
   const float Cm = fmaf(PCF(217) * dCm * Ka, dze * PCF(150), mz);
   const float wzd = Cm * (rV2 * mp.half_Sc_over_Iz);
   // clamping anti-windup (СС)
@@ -319,14 +360,17 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
   const float t0f = (float)n * hh;
   // float32 copies of the accumulated state for the stage evaluations
   const float y_h = __double2float_rn(r.h), y_Vx = __double2float_rn(r.Vx), y_Vy = __double2float_rn(r.Vy),
-              y_wz = __double2float_rn(r.wz), y_ssi = __double2float_rn(r.ssi), y_ssf = __double2float_rn(r.ssf);
-  float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf;
+              y_wz = __double2float_rn(r.wz), y_ssi = __double2float_rn(r.ssi), y_ssf = __double2float_rn(r.ssf),
+              y_th = __double2float_rn(r.th);
+  const float vref_f = __double2float_rn(r.vartheta);
+  float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf, Xf_th = y_th;
   double X_th = r.th, Xd_h = r.h, X_csi = r.csi, X_csf = r.csf;
   float a_h = 0, a_Vx = 0, a_Vy = 0, a_wz = 0, a_ssi = 0, a_ssf = 0, a_th = 0, a_x = 0;
   float a_dvi = 0, a_itse = 0;
   double a_csi = 0, a_csf = 0;
   bool memout_ss = false, memout_cs = false;
   float u_n = 0.f;
+  AtmoMx at;
 #if B747_UNROLL_STAGES
 #pragma unroll
 #else
@@ -337,8 +381,8 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
     const float t_f = s == 0 ? t0f : (s == 3 ? t0f + hh : t0f + hhalf);
     float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_itse;
     double f_csi, f_csf;
-    pass32<GEN>(sT, mp, c, s, n, X_th, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, memout_ss,
-                memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
+    pass32<GEN>(sT, mp, c, s, n, X_th, Xf_th, vref_f, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, at,
+                memout_ss, memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
     if (s == 0) {
       // update(): discrete filter, rate-limiter memory, Memory blocks, Derivative history, delay push
       if ((n % 5) == 0) r.df_x = fmaf(PCF(138), r.df_x, PCF(139) * o.td);
@@ -361,11 +405,13 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
       const float cf = (s == 2) ? hh : hhalf;
       const double cfd = (s == 2) ? kH : 0.5 * kH;
       if (s == 2) {  // integral / position signals at stage 4 = y + h*f2
-        s4.dvi = fma(kH, o.dv, r.dvi);
+        s4.dvi = r.dvi + (double)(hh * o.dvf);
         s4.itse = r.itse + (double)(hh * f_itse);
         s4.x = want_x ? (float)r.x + hh * X_Vx : 0.f;
+        X_th = fma(kH, (double)X_wz, r.th);  // theta' = wz: the full-step pass needs the float64 pitch
+      } else {
+        Xf_th = fmaf(cf, X_wz, y_th);        // half-step passes: float32 pitch
       }
-      X_th = fma(cfd, (double)X_wz, r.th);  // theta' = wz (stage value)
       X_h = fmaf(cf, f_h, y_h); X_Vx = fmaf(cf, f_Vx, y_Vx); X_Vy = fmaf(cf, f_Vy, y_Vy); X_wz = fmaf(cf, f_wz, y_wz);
       X_ssi = fmaf(cf, f_ssi, y_ssi); X_ssf = fmaf(cf, f_ssf, y_ssf);
       if (GEN) {

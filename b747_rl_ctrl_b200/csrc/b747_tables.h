@@ -98,17 +98,19 @@ inline Fast build() {
     return F;  // ok == false: the parameter set does not fit the compiled layout
   F.v.assign((size_t)CELLS * 4, 0.f);
   const float qnan = nanf("");
-  auto axis = [&](int off, const std::vector<double>& b) {
+  // `unit`: breakpoints are stored divided by it (the alpha axis is kept in radians: the DLL converts alpha to
+  // degrees with the gain P21 before the look-up, the kernel skips that multiply)
+  auto axis = [&](int off, const std::vector<double>& b, double unit) {
     const int n = (int)b.size() - 1;
     for (int i = 0; i < n; i++) {
       float* q = &F.v[(size_t)(off + i) * 4];
-      q[0] = i == 0 ? qnan : (float)b[i];
-      q[1] = i == n - 1 ? qnan : (float)b[i + 1];
-      q[2] = (float)b[i];
-      q[3] = (float)(1.0 / (b[i + 1] - b[i]));
+      q[0] = i == 0 ? qnan : (float)(b[i] / unit);
+      q[1] = i == n - 1 ? qnan : (float)(b[i + 1] / unit);
+      q[2] = (float)(b[i] / unit);
+      q[3] = (float)(unit / (b[i + 1] - b[i]));
     }
   };
-  axis(AXM, F.bM); axis(AXA, F.bA); axis(AXH, F.bH); axis(AXC, F.bC);
+  axis(AXM, F.bM, 1.0); axis(AXA, F.bA, P[21]); axis(AXH, F.bH, 1.0); axis(AXC, F.bC, 1.0);
   for (int i = 0; i < NA; i++) {
     float* q = &F.v[(size_t)(KA + i) * 4];
     q[0] = (float)O.Ka(F.bA[i]); q[1] = (float)(O.Ka(F.bA[i + 1]) - O.Ka(F.bA[i]));
@@ -154,9 +156,10 @@ inline double bil(const float* c, double f0, double f1) {
 }
 struct FastEval {
   const Fast& F;
-  void eval(double M, double a, double h, double out[5]) const {  // CYa, CXa, dCm, mz, Ka
+  void eval(double M, double a, double h, double out[5]) const {  // a in degrees; CYa, CXa, dCm, mz, Ka
+    const Orig O;
     const int iM = find(F.bM, M), iA = find(F.bA, a), iH = find(F.bH, h);
-    const double fM = frac(F, AXM, iM, M), fA = frac(F, AXA, iA, a), fH = frac(F, AXH, iH, h);
+    const double fM = frac(F, AXM, iM, M), fA = frac(F, AXA, iA, a / O.P[21]), fH = frac(F, AXH, iH, h);
     const float* q = &F.v[(size_t)(T_MA + 2 * (iA * NM + iM)) * 4];
     out[0] = bil(q, fM, fA);
     out[3] = bil(q + 4, fM, fA);
