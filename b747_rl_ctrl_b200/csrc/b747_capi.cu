@@ -33,6 +33,11 @@ struct b747_handle {
   // staging for b747_step_host
   void *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_term = nullptr;
   uint8_t* d_done = nullptr;
+  // b747_step_host pipeline: copy-in / second compute / copy-out streams and per-chunk events (created on first use)
+  cudaStream_t s_in = nullptr, s_aux = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_k;
+  cudaEvent_t ev_start = nullptr;
+  int host_chunks = 0;  // 0 = choose from n_envs
   b747_episode* d_eps = nullptr;
   double* d_metrics = nullptr;  // [n_pad][5] staging for b747_transfer_metrics
   TraceState trace;
@@ -130,6 +135,7 @@ static int fill_devcfg(const b747_cfg& c, DevCfg& d) {
   memset(&d, 0, sizeof d);
   d.n_envs = c.n_envs;
   d.n_pad = (c.n_envs + 127) / 128 * 128;
+  d.env_lo = 0; d.env_hi = c.n_envs;
   d.obs_type = c.obs_type; d.obs_dim = obs_dim_of(c.obs_type); d.rew_type = c.rew_type;
   d.ctrl_type = c.ctrl_type; d.ctrl_mode = c.ctrl_mode; d.reset_ref_mode = c.reset_ref_mode;
   d.disturbance_mode = c.disturbance_mode; d.norm_obs = c.norm_obs; d.norm_act = c.norm_act;
@@ -240,6 +246,12 @@ extern "C" int b747_destroy(b747_handle* h) {
   f32_free(h->s32);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_done); cudaFree(h->d_eps);
   if (h->own_stream) cudaStreamDestroy(h->stream);
+  for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_k) cudaEventDestroy(e);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_aux) cudaStreamDestroy(h->s_aux);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
   return B747_OK;
 }
@@ -334,18 +346,84 @@ extern "C" int b747_step(b747_handle* h, const void* act, void* obs, void* rew, 
   return B747_OK;
 }
 
+// One env step with HOST buffers.  Small batches: copy in, one launch, copy out.  Large batches run as a pipeline over
+// env chunks -- actions of chunk c+1 go up and results of chunk c-1 come down (PCIe is full duplex, the copy engines run
+// beside the SMs) while chunk c is stepped; chunks alternate between two compute streams so that the tail wave of one
+// overlaps the head of the next.  Environments are independent, so chunking cannot change any result.
+static int step_chunk(b747_handle* h, int lo, int hi, bool term, cudaStream_t s) {
+  DevCfg dc = h->dc;
+  dc.env_lo = lo; dc.env_hi = hi;
+  if (h->cfg.dtype == B747_F64)
+    launch_env_step64(dc, h->s64, (const double*)h->d_act, (double*)h->d_obs, (double*)h->d_rew, h->d_done,
+                      term ? (double*)h->d_term : nullptr, s);
+  else
+    launch_env_step32(dc, h->s32, (const float*)h->d_act, (float*)h->d_obs, (float*)h->d_rew, h->d_done,
+                      term ? (float*)h->d_term : nullptr, s);
+  h->launches++;
+  return B747_OK;
+}
+
+extern "C" int b747_set_host_chunks(b747_handle* h, int n_chunks) {
+  if (!h || n_chunks < 0 || n_chunks > 64) return fail(B747_ERR_ARG, "n_chunks must be in 0..64 (0 = automatic)");
+  h->host_chunks = n_chunks;
+  return B747_OK;
+}
+
 extern "C" int b747_step_host(b747_handle* h, const void* act, void* obs, void* rew, uint8_t* done, void* term) {
   if (!h || !act || !obs || !rew || !done) return fail(B747_ERR_ARG, "null argument");
+  if (!h->cfg.env_layer) return fail(B747_ERR_STATE, "handle was created with env_layer=0; use b747_model_step");
   CU(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)h->cfg.n_envs, es = h->elem(), od = (size_t)h->dc.obs_dim;
-  CU(cudaMemcpyAsync(h->d_act, act, es * n, cudaMemcpyHostToDevice, h->stream));
-  int rc = b747_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, term ? h->d_term : nullptr);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(obs, h->d_obs, es * n * od, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaMemcpyAsync(rew, h->d_rew, es * n, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaMemcpyAsync(done, h->d_done, n, cudaMemcpyDeviceToHost, h->stream));
-  if (term) CU(cudaMemcpyAsync(term, h->d_term, es * n * od, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  int chunks = h->host_chunks ? h->host_chunks : (n >= ((size_t)1 << 17) ? 8 : 1);
+  const size_t per = ((n + chunks - 1) / chunks + 127) / 128 * 128;  // whole thread blocks per chunk
+  chunks = (int)((n + per - 1) / per);  // whole-block rounding can empty the last chunks
+  if (chunks == 1) {
+    CU(cudaMemcpyAsync(h->d_act, act, es * n, cudaMemcpyHostToDevice, h->stream));
+    step_chunk(h, 0, (int)n, term != nullptr, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(obs, h->d_obs, es * n * od, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(rew, h->d_rew, es * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(done, h->d_done, n, cudaMemcpyDeviceToHost, h->stream));
+    if (term) CU(cudaMemcpyAsync(term, h->d_term, es * n * od, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return B747_OK;
+  }
+  if (!h->s_in) {
+    CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  }
+  while ((int)h->ev_in.size() < chunks) {
+    cudaEvent_t a, b;
+    CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_in.push_back(a); h->ev_k.push_back(b);
+  }
+  // everything queued on the handle's stream so far (resets, device-side steps) comes first
+  CU(cudaEventRecord(h->ev_start, h->stream));
+  CU(cudaStreamWaitEvent(h->s_aux, h->ev_start, 0));
+  const char* a8 = (const char*)act;
+  char *o8 = (char*)obs, *r8 = (char*)rew, *t8 = (char*)term;
+  for (int c = 0; c < chunks; c++) {
+    const size_t lo = (size_t)c * per, hi = std::min(n, lo + per), m = hi - lo;
+    CU(cudaMemcpyAsync((char*)h->d_act + es * lo, a8 + es * lo, es * m, cudaMemcpyHostToDevice, h->s_in));
+    CU(cudaEventRecord(h->ev_in[c], h->s_in));
+    cudaStream_t sc = (c & 1) ? h->s_aux : h->stream;
+    CU(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
+    step_chunk(h, (int)lo, (int)hi, term != nullptr, sc);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_k[c], sc));
+    CU(cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+    CU(cudaMemcpyAsync(o8 + es * od * lo, (char*)h->d_obs + es * od * lo, es * od * m, cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaMemcpyAsync(r8 + es * lo, (char*)h->d_rew + es * lo, es * m, cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaMemcpyAsync(done + lo, h->d_done + lo, m, cudaMemcpyDeviceToHost, h->s_out));
+    if (term) CU(cudaMemcpyAsync(t8 + es * od * lo, (char*)h->d_term + es * od * lo, es * od * m, cudaMemcpyDeviceToHost, h->s_out));
+  }
+  // later work on the handle's stream is ordered after the odd chunks too
+  CU(cudaStreamWaitEvent(h->stream, h->ev_k[chunks - 1], 0));
+  if (chunks > 1) CU(cudaStreamWaitEvent(h->stream, h->ev_k[chunks - 2], 0));
+  CU(cudaStreamSynchronize(h->s_out));
   return B747_OK;
 }
 

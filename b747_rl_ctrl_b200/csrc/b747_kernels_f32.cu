@@ -59,8 +59,8 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
     r.tf_tp = 0.f; r.sig_vzh = 0.f;
   }
   r.vartheta = 0.0;
-#pragma unroll
-  for (int k = 0; k < N_AXES; k++) r.ax[k] = 0;  // interval cache: re-searched on first use
+  r.tc = TabCache{};  // look-up cache: zero widths = nothing cached, refilled on first use
+  r.tc.ix = 0xffffffffu;
 }
 
 // `full`: also the groups a step never changes (reference, aero sums, state0) -- reset paths only.
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
   __shared__ float4 sT[kFastCells];
   __shared__ EpStatsSmem sst;
   load_tables32(sT, st.tables);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < c.n_envs;
+  const int i = c.env_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < c.env_hi;
   const size_t np = (size_t)c.n_pad;
   bool done = false;
   double ep_ret = 0.0, ep_len = 0.0;
@@ -427,10 +427,12 @@ static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s) {
   const MP32 mp = make_mp32(c.mp);
+  const int n = c.env_hi - c.env_lo;
+  if (n <= 0) return;
   if (f32_is_lean(c) && !st.trace.trk && !st.trace.rec)
-    k_env_step32<false><<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    k_env_step32<false><<<grid_for(n, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else
-    k_env_step32<true><<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    k_env_step32<true><<<grid_for(n, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
 }
 void launch_reset32(const DevCfg& c, const StateF32& st, const uint8_t* mask, const b747_episode* eps, float* obs,
                     cudaStream_t s) {

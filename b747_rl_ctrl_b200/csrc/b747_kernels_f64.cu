@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(128) k_env_step64(DevCfg c, StateF64 st, const
   __shared__ double sP[kNP];
   __shared__ EpStatsSmem sst;
   load_tables64(sP);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < c.n_envs;
+  const int i = c.env_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < c.env_hi;
   const size_t np = (size_t)c.n_pad;
   bool done = false;
   double ep_ret = 0.0, ep_len = 0.0;
@@ -391,7 +391,9 @@ void launch_transfer_metrics(const DevCfg& c, const TraceState& tr, int which, i
 
 void launch_env_step64(const DevCfg& c, const StateF64& st, const double* actions, double* obs, double* rew,
                        uint8_t* done, double* term_obs, cudaStream_t s) {
-  k_env_step64<<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, st, actions, obs, rew, done, term_obs);
+  const int n = c.env_hi - c.env_lo;
+  if (n <= 0) return;
+  k_env_step64<<<grid_for(n, 128), 128, 0, s>>>(c, st, actions, obs, rew, done, term_obs);
 }
 void launch_model_step64(const DevCfg& c, const StateF64& st, int n_steps, cudaStream_t s) {
   k_model_step64<<<grid_for(c.n_envs, 128), 128, 0, s>>>(c, st, n_steps);

@@ -15,12 +15,16 @@
 //    so these ~10 operations per pass are nearly free;
 //  * every integrator state is accumulated in float64 across steps (y += h/6 * sum), the stage
 //    values inside a step are float32;
-//  * look-ups: the five tables are re-sampled on merged axes (b747_tables.h: one Mach, one alpha, one
-//    altitude and one CYa axis instead of the DLL's eight breakpoint sets -- exact for a bilinear
-//    interpolant).  Per axis ONE 128-bit shared-memory load returns {valid-lo, valid-hi, breakpoint,
-//    1/spacing} of the cached interval; the cached interval is validated with two compares and only
-//    re-searched (incrementally) when the operand left it -- Mach, alpha and h move by ~1e-4 of an
-//    interval per pass.  Each 2-D table cell is one 128-bit load of {t00, t10-t00, t01, t11-t01};
+//  * look-ups: the five tables are re-sampled on merged, sentinel-extended axes (b747_tables.h: one Mach,
+//    one alpha, one altitude and one CYa axis instead of the DLL's eight breakpoint sets -- exact for a
+//    bilinear interpolant) and stored as polynomial coefficients in the offsets from the interval's lower
+//    breakpoint.  The current interval {bp, width} of every axis and the coefficients of the current cells
+//    live in REGISTERS (TabCache); a pass validates them with one unsigned compare per axis and evaluates
+//    each table with three FMAs.  Shared memory is touched only when an operand crossed a breakpoint (Mach,
+//    alpha and h move by ~1e-4 of an interval per pass; CYa crosses its 0.1-wide intervals more often): the
+//    refill walks to the neighbour interval and reloads the cells it addresses.  (ncu r1d: the per-pass LDS.128
+//    validation of the previous design drew 40 % of the kernel's stall samples and 72 % of the
+//    shared-memory wavefront peak.)
 //  * sin/cos(theta), atan(wb/ub) and the ISA density power are short float32 polynomials
 //    (b747_poly.h, generated + validated by tools/gen_poly.py) with libm fall-backs outside their
 //    fitted ranges; sin(alpha), cos(alpha) come from the body-axis velocity components;
@@ -55,9 +59,15 @@ static_assert((Pc(16) - Pc(17) * Pc(19)) * Pc(127) > 0.70 && (Pc(16) - Pc(18) * 
               "ISA temperature ratio leaves the range of the density polynomial (tools/gen_poly.py)");
 
 // Look-up tables: re-gridded on merged axes by the host (b747_tables.h), staged in shared memory.
-enum { AX_M = 0, AX_A, AX_H, AX_C, N_AXES };
-__host__ __device__ constexpr int axis_off(int a) { return a == AX_M ? ft::AXM : a == AX_A ? ft::AXA : a == AX_H ? ft::AXH : ft::AXC; }
 constexpr int kFastCells = ft::CELLS;
+
+// Register-resident table state of one environment: current interval of each axis and current cells.
+struct TabCache {
+  float bM, wM, bA, wA, bH, wH, bC, wC;  // lower breakpoint and width of the current interval (alpha in radians)
+  float k0, k1;                          // K_alpha = k0 + k1 dA on the current alpha interval
+  float4 cCY, cMZ, cCX, cDC;             // cells: y = (c.x + c.y d0) + (c.z + c.w d0) d1
+  uint32_t ix;                           // interval indices iM | iA << 8 | iH << 16 | iC << 24 (read by the refill only)
+};
 
 // float copies of the uniform tunables + folded constants (built on the host, b747_kernels_f32.cu)
 // Manual switches of the diagram, resolved on the host against their thresholds (P148, P9, P149)
@@ -79,7 +89,7 @@ struct RegsMx {
   double oscA[3], oscf[3];
   int tick, flags;
   uint32_t ep_idx;
-  int ax[N_AXES];                                  // cached interval of every look-up axis, as a byte offset (16*i)
+  TabCache tc;                                     // look-up state (registers only; invalid at load: widths 0)
 };
 
 struct PassMx {
@@ -127,30 +137,83 @@ __device__ __forceinline__ float alpha_of(float wb, float ub) {
   return atan2_far(-wb, ub);
 }
 
-// One axis: validate the cached interval (two compares), re-search incrementally if the operand left
-// it, return the interval record.  `off` is the byte offset 16*interval.
-template <int A>
-__device__ __forceinline__ float4 axis_lookup(const float4* __restrict__ sT, float u, int& off) {
-  const char* base = (const char*)(sT + axis_off(A));
-  float4 q = *(const float4*)(base + off);
-  while ((u < q.x) || (u >= q.y)) {  // NaN end markers / NaN operand terminate the search
-    off += (u >= q.y) ? 16 : -16;
-    q = *(const float4*)(base + off);
+// 0 <= d < w as ONE unsigned compare: a negative d has its sign bit set, NaN compares above every finite width
+__device__ __forceinline__ bool axis_miss(float d, float w) { return __float_as_uint(d) >= __float_as_uint(w); }
+
+// Walk from interval i to the one that holds u (or to the end of the axis; NaN stops at once); returns its record.
+template <int OFF, int N>
+__device__ __forceinline__ float4 axis_seek(const float4* __restrict__ sT, float u, int& i) {
+  float4 q = sT[OFF + i];
+  if (u < q.x) {
+    while (i > 0) { --i; q = sT[OFF + i]; if (!(u < q.x)) break; }
+  } else {
+    while (u - q.x >= q.y && i < N - 1) { ++i; q = sT[OFF + i]; }
   }
   return q;
 }
-
-template <int A>
-__device__ __forceinline__ float4 axis_peek(const float4* __restrict__ sT, int off) {
-  return *(const float4*)((const char*)(sT + axis_off(A)) + off);
+// first search of a launch: coarse index map of axis k (b747_tables.h), `lo`/`inv` = sentinel range of the axis
+template <int K>
+__device__ __forceinline__ int axis_guess(const float4* __restrict__ sT, float u, float lo, float inv) {
+  const int b = min(max((int)((u - lo) * inv), 0), ft::LUT_N - 1);
+  return ((const unsigned char*)(sT + ft::LUT))[K * ft::LUT_N + b];
 }
-__device__ __forceinline__ bool axis_miss(float u, const float4& q) { return (u < q.x) | (u >= q.y); }
 
-// bilinear cell {t00, t10-t00, t01, t11-t01}: look2_binlx's operation order with the differences pre-computed
-__device__ __forceinline__ float bilinear(const float4 c, float f0, float f1) {
-  const float yL = fmaf(c.y, f0, c.x);
-  const float yR = fmaf(c.w, f0, c.z);
-  return fmaf(yR - yL, f1, yL);
+__device__ __forceinline__ float bilinear(const float4 c, float d0, float d1) {
+  return fmaf(fmaf(c.w, d0, c.z), d1, fmaf(c.y, d0, c.x));
+}
+
+// Cold paths.  An operand left its cached interval (or nothing is cached yet); interval indices move incrementally (an
+// operand crosses into a NEIGHBOUR interval).  The cached record of an axis is always the one `ix` names, so cells and
+// offsets stay consistent.
+//  * Mach / alpha / h miss: their records and the three cells they address are reloaded.  ONE out-of-line copy, result
+//    through memory, so that the four unrolled stage copies of the pass stay small in the instruction cache (ncu r1f:
+//    the fully inlined form doubled the loop to 26 KB and tripled the no_instruction stalls).
+//  * CYa miss -- the common case, CYa crosses its 0.1-wide intervals with every degree of alpha: a few inline
+//    instructions move the interval and reload the CXa cell.
+struct TabMAH { float bM, wM, bA, wA, bH, wH, k0, k1; float4 cCY, cMZ, cDC; uint32_t ix; };
+
+__device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float Mach, float alpha, float h, float cy_gain,
+                                            uint32_t ix, TabMAH* __restrict__ out) {
+  int iM = ix & 31, iA = (ix >> 8) & 31, iH = (ix >> 16) & 7, iC = ix >> 24;
+  const bool empty = ix == 0xffffffffu;
+  constexpr float rad = (float)Pc(21);
+  if (empty) {
+    iM = axis_guess<0>(sT, Mach, 0.f, (float)(ft::LUT_N / ft::EXT_M_HI));
+    iA = axis_guess<1>(sT, alpha, (float)(ft::EXT_A_LO / rad), (float)(ft::LUT_N * rad / (ft::EXT_A_HI - ft::EXT_A_LO)));
+    iH = axis_guess<2>(sT, h, (float)ft::EXT_H_LO, (float)(ft::LUT_N / (ft::EXT_H_HI - ft::EXT_H_LO)));
+  }
+  TabMAH t;
+  const float4 qM = axis_seek<ft::AXM, ft::NM>(sT, Mach, iM);
+  const float4 qA = axis_seek<ft::AXA, ft::NA>(sT, alpha, iA);
+  const float4 qH = axis_seek<ft::AXH, ft::NH>(sT, h, iH);
+  t.bM = qM.x; t.wM = qM.y; t.bA = qA.x; t.wA = qA.y; t.k0 = qA.z; t.k1 = qA.w; t.bH = qH.x; t.wH = qH.y;
+  const float4* cMA = sT + ft::T_MA + 2 * (iA * ft::NM + iM);
+  t.cCY = cMA[0]; t.cMZ = cMA[1];
+  t.cDC = sT[ft::T_HM + iM * ft::NH + iH];
+  if (empty) {
+    const float CYa = bilinear(t.cCY, Mach - t.bM, alpha - t.bA) * cy_gain;
+    iC = axis_guess<3>(sT, CYa, (float)ft::EXT_C_LO, (float)(ft::LUT_N / (ft::EXT_C_HI - ft::EXT_C_LO)));
+  }
+  t.ix = (uint32_t)iM | (uint32_t)iA << 8 | (uint32_t)iH << 16 | (uint32_t)iC << 24;
+  *out = t;
+}
+
+__device__ __forceinline__ void tab_update(const float4* __restrict__ sT, float Mach, float alpha, float h, float cy_gain,
+                                           bool missMAH, TabCache& t, float& dM, float& dA, float& dH, float& CYa, float& dC) {
+  if (missMAH) {
+    TabMAH m;
+    tab_refill_mah(sT, Mach, alpha, h, cy_gain, t.ix, &m);
+    t.bM = m.bM; t.wM = m.wM; t.bA = m.bA; t.wA = m.wA; t.bH = m.bH; t.wH = m.wH; t.k0 = m.k0; t.k1 = m.k1;
+    t.cCY = m.cCY; t.cMZ = m.cMZ; t.cDC = m.cDC; t.ix = m.ix;
+    dM = Mach - t.bM; dA = alpha - t.bA; dH = h - t.bH;
+    CYa = bilinear(t.cCY, dM, dA) * cy_gain;
+  }
+  int iC = t.ix >> 24;
+  const float4 qC = axis_seek<ft::AXC, ft::NC>(sT, CYa, iC);
+  t.bC = qC.x; t.wC = qC.y;
+  t.cCX = sT[ft::T_MC + iC * ft::NM + (t.ix & 31)];
+  dC = CYa - t.bC;
+  t.ix = (t.ix & 0x00ffffffu) | (uint32_t)iC << 24;
 }
 
 // Atmosphere of one model step: evaluated in full at the major pass, carried to the three minor passes by its first
@@ -241,32 +304,23 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   }
   const float Mach = V * ia;
   o.Mach = Mach;
-  // look-ups on the merged axes (b747_tables.h): one cached interval per operand.  Fast path: three
-  // LDS.128 fetch the cached interval records, one combined predicate validates them; the incremental
-  // re-search of an operand that left its interval is rare (Mach, alpha, h move ~1e-4 of an interval per pass).
+  // look-ups on the merged axes (b747_tables.h) from the register cache.  The cache is validated with the offsets
+  // themselves (the CYa axis speculatively, from the cached CYa cell); the refill is rare and out of line.
   // The alpha axis is stored in radians (breakpoints / P21), so no conversion to degrees is needed.
-  float4 qM = axis_peek<AX_M>(sT, r.ax[AX_M]);
-  float4 qA = axis_peek<AX_A>(sT, r.ax[AX_A]);
-  float4 qH = axis_peek<AX_H>(sT, r.ax[AX_H]);
-  if (axis_miss(Mach, qM) | axis_miss(alpha, qA) | axis_miss(h, qH)) {
-    qM = axis_lookup<AX_M>(sT, Mach, r.ax[AX_M]);
-    qA = axis_lookup<AX_A>(sT, alpha, r.ax[AX_A]);
-    qH = axis_lookup<AX_H>(sT, h, r.ax[AX_H]);
-  }
-  const float fM = (Mach - qM.z) * qM.w, fA = (alpha - qA.z) * qA.w, fH = (h - qH.z) * qH.w;
-  const char* sB = (const char*)sT;
-  // CYa and mz share the (Mach, alpha) cell: two adjacent 128-bit loads
-  const float4* cMA = (const float4*)(sB + ft::T_MA * 16 + (r.ax[AX_A] * ft::NM + r.ax[AX_M]) * 2);
-  float CYa = bilinear(cMA[0], fM, fA);
-  float mz = bilinear(cMA[1], fM, fA);
-  if (GEN) CYa *= r.sumA[1];
-  const float4 qC = axis_lookup<AX_C>(sT, CYa, r.ax[AX_C]);
-  float CXa = bilinear(*(const float4*)(sB + ft::T_MC * 16 + r.ax[AX_C] * ft::NM + r.ax[AX_M]), fM, (CYa - qC.z) * qC.w);
+  TabCache& tc = r.tc;
+  const float cy_gain = GEN ? r.sumA[1] : 1.0f;
+  float dM = Mach - tc.bM, dA = alpha - tc.bA, dH = h - tc.bH;
+  float CYa = bilinear(tc.cCY, dM, dA);
+  if (GEN) CYa *= cy_gain;
+  float dC = CYa - tc.bC;
+  const bool missMAH = axis_miss(dM, tc.wM) | axis_miss(dA, tc.wA) | axis_miss(dH, tc.wH);
+  if (missMAH | axis_miss(dC, tc.wC)) tab_update(sT, Mach, alpha, h, cy_gain, missMAH, tc, dM, dA, dH, CYa, dC);
+  float mz = bilinear(tc.cMZ, dM, dA);
+  float CXa = bilinear(tc.cCX, dM, dC);
   if (GEN) CXa *= r.sumA[0];
   o.CYa = CYa; o.CXa = CXa;
-  float dCm = bilinear(*(const float4*)(sB + ft::T_HM * 16 + r.ax[AX_M] * ft::NH + r.ax[AX_H]), fH, fM);
-  const float4 kc = *(const float4*)(sB + ft::KA * 16 + r.ax[AX_A]);
-  float Ka = fmaf(kc.y, fA, kc.x);
+  float dCm = bilinear(tc.cDC, dH, dM);
+  float Ka = fmaf(tc.k1, dA, tc.k0);
   if (GEN) { dCm *= r.sumA[3]; Ka *= r.sumA[4]; mz *= r.sumA[2]; }
   o.dCm = dCm; o.K_alpha = Ka; o.mz = mz;
   // aerodynamic + thrust acceleration in body axes, straight from the body velocity components:

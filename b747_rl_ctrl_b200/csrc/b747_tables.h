@@ -6,17 +6,29 @@
 // three different breakpoint sets and alpha on three others -- seven interval searches per diagram pass.
 //
 // A bilinear interpolant stays bilinear on every sub-cell of its grid, and look2_binlx extrapolates the
-// end cells linearly, so re-sampling each table on the UNION of the breakpoint sets of an operand is
-// exact: one Mach axis (16 intervals), one alpha axis (21), the altitude axis (4) and the CYa axis (13)
-// serve all five tables, with one interval search and one fraction per operand.  The tables are
-// re-sampled here in float64 from model_simple_P and rounded once to float32.
+// end cells linearly (the end cell's own polynomial), so re-sampling each table on the UNION of the
+// breakpoint sets of an operand is exact: one Mach axis, one alpha axis, the altitude axis and the CYa axis
+// serve all five tables, with one interval and one offset per operand.  Each merged axis is also EXTENDED by
+// one sentinel interval per open end (Mach up to 2, alpha -40..75 deg, h -4..24 km, CYa -4..4) whose cells
+// carry the end cell's polynomial: inside the sentinels an operand never "leaves the table", so the kernel's
+// interval cache (below) stays valid while the DLL would be extrapolating.  Beyond the sentinels the end
+// cell is used as is (linear extrapolation, exactly look2_binlx) and merely never caches.
+// The tables are re-sampled here in float64 from model_simple_P and rounded once to float32.
+//
+// Cells are stored as polynomial coefficients in the OFFSETS d = u - bp[i] from the interval's lower
+// breakpoint (not in the 0..1 fractions):  y = (c0 + c1 d0) + (c2 + c3 d0) d1  -- three FMAs, no fraction
+// multiply, no yR - yL subtraction.  The kernel keeps {bp, width} of the current interval of every axis and
+// the coefficients of the current cells IN REGISTERS; a pass validates the cache with one unsigned compare
+// per axis (as_uint(d) < as_uint(width)  <=>  0 <= d < width) and touches shared memory only when an
+// operand crossed a breakpoint (Mach, alpha, h move ~1e-4 of an interval per pass).
 //
 // Layout (float4 units, staged into shared memory by every block of k_env_step32):
-//   axis record, one per interval i:      {lo, hi, bp[i], 1/(bp[i+1]-bp[i])}; lo of the first / hi of the
-//                                         last interval are NaN (never "left": end cells extrapolate)
-//   K_alpha record per alpha interval:    {t[i], t[i+1]-t[i], 0, 0}
-//   2-D cell (i0 along axis 0, i1 axis 1): {t00, t10-t00, t01, t11-t01}
+//   axis record, one per interval i:      {bp[i], bp[i+1]-bp[i], k0, k1}; (k0, k1) = K_alpha(alpha) = k0 + k1 d
+//                                         on the alpha axis, 0 elsewhere.  The alpha axis is in radians.
+//   2-D cell (i0 along axis 0, i1 axis 1): {c0, c1, c2, c3}
 //   CYa and mz share both axes; their cells are interleaved (2 float4 per cell).
+//   coarse index map per axis: LUT_N bytes, bucket b of the sentinel range -> interval holding the bucket's lower
+//                                         edge; the first search of a launch starts there (the kernel then walks 0..2 steps)
 // Host-only code (no CUDA types); the device side reads it through the offsets below.
 #pragma once
 #include <math.h>
@@ -30,12 +42,17 @@
 namespace b747 {
 namespace ft {
 
-constexpr int NM = 16, NA = 21, NH = 4, NC = 13;  // intervals per merged axis (checked by build())
-constexpr int AXM = 0, AXA = AXM + NM, AXH = AXA + NA, AXC = AXH + NH, KA = AXC + NC;  // float4 offsets
-constexpr int T_HM = KA + NA;            // dCm cells  [iM][iH]
-constexpr int T_MC = T_HM + NM * NH;     // CXa cells  [iC][iM]
-constexpr int T_MA = T_MC + NC * NM;     // CYa,mz cells [iA][iM][2]
-constexpr int CELLS = T_MA + 2 * NA * NM;  // 1019 float4 = 16304 bytes
+constexpr int NM = 17, NA = 23, NH = 6, NC = 15;  // intervals per merged + extended axis (checked by build())
+constexpr int AXM = 0, AXA = AXM + NM, AXH = AXA + NA, AXC = AXH + NH;  // float4 offsets
+constexpr int T_HM = AXC + NC;           // dCm cells  [iM][iH]      d0 = h offset,    d1 = Mach offset
+constexpr int T_MC = T_HM + NM * NH;     // CXa cells  [iC][iM]      d0 = Mach offset, d1 = CYa offset
+constexpr int T_MA = T_MC + NC * NM;     // CYa,mz cells [iA][iM][2] d0 = Mach offset, d1 = alpha offset (rad)
+constexpr int LUT = T_MA + 2 * NA * NM;   // 4 coarse index maps (Mach, alpha, h, CYa), LUT_N bytes each
+constexpr int LUT_N = 64;
+constexpr int CELLS = LUT + 4 * LUT_N / 16;  // 1216 float4 = 19456 bytes
+// sentinel breakpoints (alpha in degrees, like the DLL's tables)
+constexpr double EXT_M_HI = 2.0, EXT_A_LO = -40.0, EXT_A_HI = 75.0, EXT_H_LO = -4000.0, EXT_H_HI = 24000.0, EXT_C_LO = -4.0,
+                 EXT_C_HI = 4.0;
 
 // ---- float64 restatement of the DLL's interpolation (test oracle for the re-gridding) ----
 inline void prelook(double u, const double* bp, int maxIndex, int& idx, double& frac) {
@@ -73,16 +90,18 @@ struct Orig {
 };
 
 struct Fast {
-  std::vector<double> bM, bA, bH, bC;  // merged breakpoints
+  std::vector<double> bM, bA, bH, bC;  // merged + extended breakpoints (alpha in degrees)
   std::vector<float> v;                // CELLS * 4 floats
   bool ok = false;
 };
 
-inline std::vector<double> merged(std::initializer_list<std::pair<const double*, int>> sets) {
+inline std::vector<double> merged(std::initializer_list<std::pair<const double*, int>> sets, double ext_lo, double ext_hi) {
   std::vector<double> r;
   for (auto& s : sets) r.insert(r.end(), s.first, s.first + s.second);
   std::sort(r.begin(), r.end());
   r.erase(std::unique(r.begin(), r.end()), r.end());
+  if (ext_lo < r.front()) r.insert(r.begin(), ext_lo);
+  if (ext_hi > r.back()) r.push_back(ext_hi);
   return r;
 }
 
@@ -90,84 +109,96 @@ inline Fast build() {
   const Orig O;
   const double* P = O.P;
   Fast F;
-  F.bM = merged({{P + 42, 4}, {P + 108, 4}, {P + 206, 10}, {P + 276, 4}});
-  F.bA = merged({{P + 46, 5}, {P + 225, 7}, {P + 280, 11}});
-  F.bH.assign(P + 201, P + 206);
-  F.bC.assign(P + 112, P + 126);
+  // Mach is a speed ratio: the merged axis starts at its first breakpoint 0, no lower sentinel
+  F.bM = merged({{P + 42, 4}, {P + 108, 4}, {P + 206, 10}, {P + 276, 4}}, 0.0, EXT_M_HI);
+  F.bA = merged({{P + 46, 5}, {P + 225, 7}, {P + 280, 11}}, EXT_A_LO, EXT_A_HI);
+  F.bH = merged({{P + 201, 5}}, EXT_H_LO, EXT_H_HI);
+  F.bC = merged({{P + 112, 14}}, EXT_C_LO, EXT_C_HI);
   if ((int)F.bM.size() != NM + 1 || (int)F.bA.size() != NA + 1 || (int)F.bH.size() != NH + 1 || (int)F.bC.size() != NC + 1)
     return F;  // ok == false: the parameter set does not fit the compiled layout
   F.v.assign((size_t)CELLS * 4, 0.f);
-  const float qnan = nanf("");
   // `unit`: breakpoints are stored divided by it (the alpha axis is kept in radians: the DLL converts alpha to
   // degrees with the gain P21 before the look-up, the kernel skips that multiply)
+  const double rad = P[21];
   auto axis = [&](int off, const std::vector<double>& b, double unit) {
     const int n = (int)b.size() - 1;
     for (int i = 0; i < n; i++) {
       float* q = &F.v[(size_t)(off + i) * 4];
-      q[0] = i == 0 ? qnan : (float)(b[i] / unit);
-      q[1] = i == n - 1 ? qnan : (float)(b[i + 1] / unit);
-      q[2] = (float)(b[i] / unit);
-      q[3] = (float)(unit / (b[i + 1] - b[i]));
+      q[0] = (float)(b[i] / unit);
+      q[1] = (float)((b[i + 1] - b[i]) / unit);
     }
   };
-  axis(AXM, F.bM, 1.0); axis(AXA, F.bA, P[21]); axis(AXH, F.bH, 1.0); axis(AXC, F.bC, 1.0);
-  for (int i = 0; i < NA; i++) {
-    float* q = &F.v[(size_t)(KA + i) * 4];
-    q[0] = (float)O.Ka(F.bA[i]); q[1] = (float)(O.Ka(F.bA[i + 1]) - O.Ka(F.bA[i]));
+  axis(AXM, F.bM, 1.0); axis(AXA, F.bA, rad); axis(AXH, F.bH, 1.0); axis(AXC, F.bC, 1.0);
+  for (int i = 0; i < NA; i++) {  // K_alpha rides in the alpha axis record
+    float* q = &F.v[(size_t)(AXA + i) * 4];
+    const double k0 = O.Ka(F.bA[i]), k1 = O.Ka(F.bA[i + 1]);
+    q[2] = (float)k0; q[3] = (float)((k1 - k0) / ((F.bA[i + 1] - F.bA[i]) / rad));
   }
-  auto cell = [&](float* q, double t00, double t10, double t01, double t11) {
-    q[0] = (float)t00; q[1] = (float)(t10 - t00); q[2] = (float)t01; q[3] = (float)(t11 - t01);
+  // corner values -> coefficients in the offsets; w0, w1 = interval widths in the kernel's units
+  auto cell = [&](float* q, double t00, double t10, double t01, double t11, double w0, double w1) {
+    q[0] = (float)t00; q[1] = (float)((t10 - t00) / w0); q[2] = (float)((t01 - t00) / w1);
+    q[3] = (float)(((t11 - t01) - (t10 - t00)) / (w0 * w1));
   };
+  auto wd = [](const std::vector<double>& b, int i, double unit) { return (b[i + 1] - b[i]) / unit; };
   for (int iM = 0; iM < NM; iM++)
     for (int iH = 0; iH < NH; iH++)
       cell(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], O.dCm(F.bH[iH], F.bM[iM]), O.dCm(F.bH[iH + 1], F.bM[iM]),
-           O.dCm(F.bH[iH], F.bM[iM + 1]), O.dCm(F.bH[iH + 1], F.bM[iM + 1]));
+           O.dCm(F.bH[iH], F.bM[iM + 1]), O.dCm(F.bH[iH + 1], F.bM[iM + 1]), wd(F.bH, iH, 1.0), wd(F.bM, iM, 1.0));
   for (int iC = 0; iC < NC; iC++)
     for (int iM = 0; iM < NM; iM++)
       cell(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], O.CXa(F.bM[iM], F.bC[iC]), O.CXa(F.bM[iM + 1], F.bC[iC]),
-           O.CXa(F.bM[iM], F.bC[iC + 1]), O.CXa(F.bM[iM + 1], F.bC[iC + 1]));
+           O.CXa(F.bM[iM], F.bC[iC + 1]), O.CXa(F.bM[iM + 1], F.bC[iC + 1]), wd(F.bM, iM, 1.0), wd(F.bC, iC, 1.0));
   for (int iA = 0; iA < NA; iA++)
     for (int iM = 0; iM < NM; iM++) {
       float* q = &F.v[(size_t)(T_MA + 2 * (iA * NM + iM)) * 4];
       cell(q, O.CYa(F.bM[iM], F.bA[iA]), O.CYa(F.bM[iM + 1], F.bA[iA]), O.CYa(F.bM[iM], F.bA[iA + 1]),
-           O.CYa(F.bM[iM + 1], F.bA[iA + 1]));
+           O.CYa(F.bM[iM + 1], F.bA[iA + 1]), wd(F.bM, iM, 1.0), wd(F.bA, iA, rad));
       cell(q + 4, O.mz(F.bM[iM], F.bA[iA]), O.mz(F.bM[iM + 1], F.bA[iA]), O.mz(F.bM[iM], F.bA[iA + 1]),
-           O.mz(F.bM[iM + 1], F.bA[iA + 1]));
+           O.mz(F.bM[iM + 1], F.bA[iA + 1]), wd(F.bM, iM, 1.0), wd(F.bA, iA, rad));
     }
+  auto lut = [&](int k, const std::vector<double>& b) {
+    unsigned char* L = reinterpret_cast<unsigned char*>(&F.v[(size_t)LUT * 4]) + k * LUT_N;
+    const int n = (int)b.size() - 1;
+    for (int j = 0; j < LUT_N; j++) {
+      const double u = b.front() + (b.back() - b.front()) * j / LUT_N;
+      int i = 0;
+      while (i < n - 1 && u >= b[i + 1]) i++;
+      L[j] = (unsigned char)i;
+    }
+  };
+  lut(0, F.bM); lut(1, F.bA); lut(2, F.bH); lut(3, F.bC);
   F.ok = true;
   return F;
 }
 
 // ---- evaluation of the fast layout on the host (float64 arithmetic on the float32 entries): what the
 // kernel computes, minus its float32 rounding.  Used by b747_selftest_tables(). ----
-inline int find(const std::vector<double>& b, double u) {
-  const int n = (int)b.size() - 1;
+// interval search on the float32 records, as the kernel's axis_find does: largest i with bp[i] <= u
+inline int find(const Fast& F, int off, int n, double u) {
   int i = 0;
-  while (i < n - 1 && u >= b[i + 1]) i++;
+  for (int j = 1; j < n; j++)
+    if (u >= (double)F.v[(size_t)(off + j) * 4]) i = j;
   return i;
 }
-inline double frac(const Fast& F, int off, int i, double u) {
-  const float* q = &F.v[(size_t)(off + i) * 4];
-  return (u - (double)q[2]) * (double)q[3];
-}
-inline double bil(const float* c, double f0, double f1) {
-  const double yL = c[0] + f0 * c[1], yR = c[2] + f0 * c[3];
-  return yL + f1 * (yR - yL);
+inline double bil(const float* c, double d0, double d1) {
+  return ((double)c[0] + (double)c[1] * d0) + ((double)c[2] + (double)c[3] * d0) * d1;
 }
 struct FastEval {
   const Fast& F;
   void eval(double M, double a, double h, double out[5]) const {  // a in degrees; CYa, CXa, dCm, mz, Ka
     const Orig O;
-    const int iM = find(F.bM, M), iA = find(F.bA, a), iH = find(F.bH, h);
-    const double fM = frac(F, AXM, iM, M), fA = frac(F, AXA, iA, a / O.P[21]), fH = frac(F, AXH, iH, h);
+    const double ar = a / O.P[21];
+    const int iM = find(F, AXM, NM, M), iA = find(F, AXA, NA, ar), iH = find(F, AXH, NH, h);
+    auto off = [&](int ax, int i, double u) { return u - (double)F.v[(size_t)(ax + i) * 4]; };
+    const double dM = off(AXM, iM, M), dA = off(AXA, iA, ar), dH = off(AXH, iH, h);
     const float* q = &F.v[(size_t)(T_MA + 2 * (iA * NM + iM)) * 4];
-    out[0] = bil(q, fM, fA);
-    out[3] = bil(q + 4, fM, fA);
-    const int iC = find(F.bC, out[0]);
-    out[1] = bil(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], fM, frac(F, AXC, iC, out[0]));
-    out[2] = bil(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], fH, fM);
-    const float* k = &F.v[(size_t)(KA + iA) * 4];
-    out[4] = k[0] + fA * k[1];
+    out[0] = bil(q, dM, dA);
+    out[3] = bil(q + 4, dM, dA);
+    const int iC = find(F, AXC, NC, out[0]);
+    out[1] = bil(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], dM, off(AXC, iC, out[0]));
+    out[2] = bil(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], dH, dM);
+    const float* k = &F.v[(size_t)(AXA + iA) * 4];
+    out[4] = (double)k[2] + dA * (double)k[3];
   }
 };
 

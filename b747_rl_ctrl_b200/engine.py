@@ -161,6 +161,10 @@ class BatchEngine:
             return obs, rew, done, terminal_obs
         return obs, rew, done
 
+    def set_host_chunks(self, n_chunks):
+        """Chunks of step_host's copy/compute pipeline: 0 = automatic, 1 = one launch."""
+        check(self._L.b747_set_host_chunks(self._h, int(n_chunks)))
+
     def model_step(self, n_steps=1):
         check(self._L.b747_model_step(self._h, int(n_steps)))
 

@@ -238,7 +238,7 @@ def run_cuda(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n_total * e2e_steps / float(te.item())
-    e2e_launches = e2e_steps + 3
+    e2e_launches = eng.launch_count - launches0 - launches
 
     # ---- the only cross-GPU quantity: episode statistics, reduced once
     stats = reduce_episode_stats(eng.episode_stats())
@@ -251,6 +251,28 @@ def run_cuda(args, rank, local_rank, world):
 
     peak, peak_src = _peaks()
     kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
+    # ---- the same kernel at K = 1 (Controller's default sample_time = dt): the HBM-bound end of the K axis
+    # (only near K = 1 can the step approach the HBM roof; reported beside the K = 10 headline)
+    k1 = None
+    if world == 1:
+        e1 = E.BatchEngine(n_envs=n_local, dtype=E.F32, device=local_rank, sample_time=0.01, seed=1, auto_reset=True)
+        e1.use_stream(stream.cuda_stream)
+        e1.reset(obs)
+        for i in range(5):
+            e1.step(pool[i % 8], obs, rew, done)
+        n1 = max(20, min(args.steps, 200))
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev1[0].record()
+        for i in range(n1):
+            e1.step(pool[i % 8], obs, rew, done)
+        ev1[1].record()
+        torch.cuda.synchronize()
+        ms1 = ev1[0].elapsed_time(ev1[1]) / n1
+        ach1 = BYTES_PER_ENV_STEP * n_local / (ms1 * 1e-3) / 1e9
+        k1 = {"substeps": 1, "kernel_ms": ms1, "env_steps_per_s": n_local / (ms1 * 1e-3), "achieved": ach1, "peak": peak,
+              "unit": "GB/s", "frac": ach1 / peak, "steps": n1}
+        e1.close()
     achieved = BYTES_PER_ENV_STEP * n_local / (kernel_ms * 1e-3) / 1e9
     prof = {}
     pj = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -265,7 +287,7 @@ def run_cuda(args, rank, local_rank, world):
                 "kernel": "b747::k_env_step32<false>", "kernel_ms": kernel_ms,
                 "note": ("K=10 substeps make the kernel FP32/XU-pipe bound, not HBM bound (SURVEY.md 8d); "
                          "pipe utilisation from ncu is in profiles/"),
-                "pipes": prof.get("pipes")}
+                "pipes": prof.get("pipes"), "k1": k1}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -274,7 +296,9 @@ def run_cuda(args, rank, local_rank, world):
                        "mixed_precision": "f32 aero/trig/tables, f64 integrator accumulation and pitch-error chain"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
-                    "d2h_bytes_per_step": (12 + 4 + 1) * n_local, "steps": e2e_steps, "api": "b747_step_host (C ABI, pinned host buffers)"},
+                    "d2h_bytes_per_step": (12 + 4 + 1) * n_local, "steps": e2e_steps,
+                    "api": "b747_step_host (C ABI, pinned host buffers; 8-chunk copy/step/copy pipeline)",
+                    "gpu_launches": int(e2e_launches)},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "episode_stats": summarize(stats)}

@@ -114,8 +114,12 @@ int b747_reset_to(b747_handle *h, const b747_episode *episodes_host, void *obs_d
 int b747_step(b747_handle *h, const void *actions_dev, void *obs_dev, void *rew_dev, uint8_t *done_dev,
               void *terminal_obs_dev);
 /* Same call with HOST buffers (pinned or pageable): H2D of actions, the step, D2H of obs/rew/done,
- * stream-synchronised on return.  This is the call a ctypes/gym user makes. */
+ * synchronised on return.  This is the call a ctypes/gym user makes.  Batches of >= 128 Ki envs are
+ * pipelined over env chunks (copy-in, step and copy-out of neighbouring chunks overlap; pinned buffers
+ * are needed for the overlap, pageable ones still work); results are identical to the one-launch form. */
 int b747_step_host(b747_handle *h, const void *actions, void *obs, void *rew, uint8_t *done, void *terminal_obs);
+/* Number of chunks of b747_step_host's pipeline: 0 = automatic (8 from 128 Ki envs, else 1), 1 = no pipeline. */
+int b747_set_host_chunks(b747_handle *h, int n_chunks);
 
 /* Raw model stepping (Model.step xN, core/model.py:247-250): no action law, no reward (f64 handles).
  * b747_model_initialize == Model.initialize (core/model.py:238-244): re-reads state0_*, zeroes time,

@@ -203,6 +203,35 @@ def test_reset_mask_and_reset_to():
     assert np.allclose(e2.get("q3"), [0.0, math.sin(0.01)]) and list(e2.get("tick")) == [0, 0]
 
 
+@pytest.mark.parametrize("dtype_name,n", [("F32", 5000), ("F64", 1300)])
+def test_step_host_pipeline_equals_one_launch(dtype_name, n):
+    """b747_step_host's chunked copy/compute pipeline returns bit-identical results to the one-launch form
+    (ragged last chunk, auto-reset inside the run, terminal observations)."""
+    from b747_rl_ctrl_b200 import engine as E
+    dtype = getattr(E, dtype_name)
+    engs = [E.BatchEngine(n_envs=n, dtype=dtype, seed=5, sample_time=0.05, tk=0.4) for _ in range(2)]
+    engs[0].set_host_chunks(1)
+    engs[1].set_host_chunks(7)
+    for e in engs:
+        e.reset()
+    rng = np.random.default_rng(1)
+    for k in range(20):
+        a = rng.uniform(-1, 1, n)
+        res = []
+        for e in engs:
+            term = np.zeros((n, e.obs_dim), e.np_dtype)
+            res.append(e.step_host(a, terminal_obs=term))
+        for x, y in zip(res[0], res[1]):
+            assert np.array_equal(x, y), k
+    assert res[0][2].any() or k > 8
+    s0, s1 = engs[0].episode_stats(), engs[1].episode_stats()  # float64 atomics: summation order differs
+    assert s0[0] == s1[0] and s0[2] == s1[2] and np.allclose(s0, s1, rtol=1e-12)
+    per = -(-(-(-n // 7)) // 128) * 128  # whole thread blocks per chunk
+    assert engs[1].launch_count - engs[0].launch_count == 20 * (-(-n // per) - 1)
+    for e in engs:
+        e.close()
+
+
 def test_ppo_learns_on_gpu_vecenv():
     """BASELINE configs[4] in miniature: PPO (SB3-default hyper-parameters restated in torch) on 8192 GPU environments
     improves the episode return well beyond the untrained policy within a few seconds."""

@@ -21,8 +21,14 @@ txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(txt)))
 hdr = rows[1]
 iS, iE, iSm = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
-sass = [(r[iS].strip(), int(r[iE] or 0), int(r[iSm] or 0)) for r in rows[2:] if len(r) > iE]
-warps = max(n for _, n, _ in sass)
+body = []
+for r in rows[2:]:
+    if r and r[0] == "Kernel Name":  # a second captured launch follows: keep the first
+        break
+    body.append(r)
+sass = [(r[iS].strip(), int(r[iE] or 0), int(r[iSm] or 0)) for r in body if len(r) > iE]
+warps = sass[0][1]  # the first instruction runs once per warp
+print('stall samples total', sum(x for _, _, x in sass))
 
 # line info from the cubin
 tmp = tempfile.mkdtemp()
