@@ -195,6 +195,22 @@ __device__ inline void block_episode_stats(EpStatsSmem& sm, bool done, double ep
   }
 }
 
+// Warp-level form for persistent kernels: no block barrier per tile; done lanes are found with a ballot, reduced with
+// shuffles and added to the block's shared-memory partials (flushed to HBM once, when the block has finished).
+__device__ inline void warp_episode_stats(double* s_stats, bool done, double ep_ret, double ep_len) {
+  const unsigned full = 0xffffffffu;
+  if (!__ballot_sync(full, done)) return;  // warp-uniform
+  double v0 = done ? 1.0 : 0.0, v1 = done ? ep_ret : 0.0, v2 = done ? ep_len : 0.0, v3 = done ? ep_ret * ep_ret : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v0 += __shfl_xor_sync(full, v0, o); v1 += __shfl_xor_sync(full, v1, o);
+    v2 += __shfl_xor_sync(full, v2, o); v3 += __shfl_xor_sync(full, v3, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(s_stats + 0, v0); atomicAdd(s_stats + 1, v1); atomicAdd(s_stats + 2, v2); atomicAdd(s_stats + 3, v3);
+  }
+}
+
 __device__ inline double nan_to_num(double x) {  // np.nan_to_num (core/model.py:167-168)
   if (x != x) return 0.0;
   if (isinf(x)) return x > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;

@@ -154,12 +154,20 @@ template <bool GEN>
 __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                     uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
+  // Persistent warps: the launch fills the GPU once (blocks = SMs x resident blocks per SM), the tables are staged into
+  // shared memory once per block, and every warp then walks its own stride of 32-env tiles with no block-level
+  // synchronisation until the episode statistics are flushed at the very end.
   __shared__ float4 sT[kFastCells];
-  __shared__ EpStatsSmem sst;
+  __shared__ double s_stats[4];
+  if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
   load_tables32(sT, st.tables);
-  const int i = c.env_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < c.env_hi;
   const size_t np = (size_t)c.n_pad;
+  const int lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
+  const int n_tiles = (c.env_hi - c.env_lo + 31) >> 5;
+#pragma unroll 1
+  for (int wt = blockIdx.x * warps_per_block + (threadIdx.x >> 5); wt < n_tiles; wt += gridDim.x * warps_per_block) {
+  const int i = c.env_lo + wt * 32 + lane;
+  const bool live = i < c.env_hi;
   bool done = false;
   double ep_ret = 0.0, ep_len = 0.0;
   if (live) {
@@ -328,7 +336,10 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
     }
     store_mx<GEN>(st, np, i, r, full_store);
   }
-  block_episode_stats(sst, done, ep_ret, ep_len, st.stats);
+  warp_episode_stats(s_stats, done, ep_ret, ep_len);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && s_stats[threadIdx.x] != 0.0) atomicAdd(st.stats + threadIdx.x, s_stats[threadIdx.x]);
 }
 
 template <bool GEN>
@@ -424,15 +435,36 @@ void f32_free(StateF32& s) {
 
 static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 
+#ifndef B747_PERSISTENT
+#define B747_PERSISTENT 1  // 0: one 128-env tile per block (grid = all tiles)
+#endif
+// grid of the step kernel: enough blocks to fill every SM at the kernel's occupancy, never more than the tiles need
+template <bool GEN>
+static int step_grid(int n) {
+  const int need = grid_for(n, 128);
+  if (!B747_PERSISTENT) return need;
+  static int resident[64] = {0};  // per device: SMs x blocks per SM
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return need;
+  if (!resident[dev]) {
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step32<GEN>, 128, 0);
+    resident[dev] = sms > 0 && per_sm > 0 ? sms * per_sm : need;
+  }
+  return need < resident[dev] ? need : resident[dev];
+}
+
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s) {
   const MP32 mp = make_mp32(c.mp);
   const int n = c.env_hi - c.env_lo;
   if (n <= 0) return;
   if (f32_is_lean(c) && !st.trace.trk && !st.trace.rec)
-    k_env_step32<false><<<grid_for(n, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    k_env_step32<false><<<step_grid<false>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else
-    k_env_step32<true><<<grid_for(n, 128), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    k_env_step32<true><<<step_grid<true>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
 }
 void launch_reset32(const DevCfg& c, const StateF32& st, const uint8_t* mask, const b747_episode* eps, float* obs,
                     cudaStream_t s) {

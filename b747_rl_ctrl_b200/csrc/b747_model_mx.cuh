@@ -222,12 +222,19 @@ __device__ __forceinline__ void tab_update(const float4* __restrict__ sT, float 
 // (0 m, 11 km) sees a one-off slope error of ~1e-5 relative, on a force that acts for 10 ms.
 struct AtmoMx { float h0, rho0, ia0, s_rho, s_ia; };
 
+// Trigonometry of one model step: sin/cos of the (folded) pitch and the angle of attack are evaluated in full at the major
+// pass and carried to the three minor passes by their exact increments -- the pitch moves by delta = wz h (<= a few 1e-2
+// rad even for a tumbling airframe), so sin/cos follow by a rotation with short series for sin/cos(delta), and alpha by
+// the angle between the body-velocity vectors of the two passes (asin of their normalised cross product).  Both are
+// more accurate than re-evaluating the float32 polynomials (no argument rounding), and need no range checks.
+struct TrigMx { float sn, cs, thf, sgn, ub, wb, rV, alpha; double thd; };
+
 // One pass over the diagram at a stage state.  stage: 0 major, 1/2 half steps, 3 full step.
 // Passes 0 and 3 -- the ones whose pitch error is differenced by the Derivative blocks, observed and rewarded -- carry
 // the pitch angle and the pitch error in float64 (th_d); the half-step passes only feed float32 RK4 sums and use th_f.
 template <bool GEN>
 __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, int stage, int n,
-                                       double th_d, float th_f, float vref_f, float t_f, float h, double h_d, float Vx,
+                                       double th_d, float dth, TrigMx& tg, float vref_f, float t_f, float h, double h_d, float Vx,
                                        float Vy, float wz, float ssi, float ssf, double csi, double csf, RegsMx& r,
                                        AtmoMx& at, bool& memout_ss, bool& memout_cs, PassMx& o, float& f_h, float& f_Vx,
                                        float& f_Vy, float& f_wz, float& f_ssi, float& f_ssf, double& f_csi, double& f_csf,
@@ -237,34 +244,46 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   // attitude.  Beyond +-90 deg the DLL's pitch asin(sin(theta)) folds back: with k = round(theta/pi) and
   // r = theta - k*pi (two-constant Cody-Waite reduction) asin(sin(theta)) = (-1)^k r, and the DLL's sin/cos of the
   // folded pitch are sin(theta) and |cos(theta)| = cos(r).  Rare, cheap, and the polynomial covers the folded range.
-  float thf;
+  // The folded pitch is continuous in theta with slope sgn = (-1)^k, which is what the minor passes advance it with.
+  float thf, sn, cs;
   double th_fold = th_d;
   static_assert(poly::SINCOS_MAX >= 1.57079632679f, "sin/cos polynomial must cover the unfolded pitch range");
   if (dbl) {
     thf = __double2float_rn(th_d);
+    float sgn = 1.0f;
     if (fabsf(thf) > 1.57079632679f) {
       const double k = rint(th_d * 0.318309886183790671538);
       double rr = fma(-k, 3.141592653589793116, th_d);
       rr = fma(-k, 1.2246467991473532e-16, rr);
-      th_fold = (((int)k) & 1) ? -rr : rr;
+      const bool odd = ((int)k) & 1;
+      th_fold = odd ? -rr : rr;
+      sgn = odd ? -1.0f : 1.0f;
       thf = __double2float_rn(th_fold);
     }
-  } else {
-    thf = th_f;
-    if (fabsf(thf) > 1.57079632679f) {
-      const float k = rintf(thf * 0.318309886f);
-      float rr = fmaf(-k, 3.14159274f, thf);
-      rr = fmaf(-k, -8.74227766e-8f, rr);
-      thf = (((int)k) & 1) ? -rr : rr;
-    }
+    if (major) tg.sgn = sgn;
   }
-  float sn, cs;
-  {
+  if (major) {
     const float z = thf * thf;
     float ps = fmaf(poly::SIN4, z, poly::SIN3); ps = fmaf(ps, z, poly::SIN2); ps = fmaf(ps, z, poly::SIN1); ps = fmaf(ps, z, poly::SIN0);
     float pc = fmaf(poly::COS4, z, poly::COS3); pc = fmaf(pc, z, poly::COS2); pc = fmaf(pc, z, poly::COS1); pc = fmaf(pc, z, poly::COS0);
     sn = fmaf(thf * z, ps, thf);
     cs = fmaf(z, pc, 1.0f);
+    tg.sn = sn; tg.cs = cs; tg.thf = thf; tg.thd = th_fold;
+  } else {
+    // increment of the folded pitch since the major pass: exact difference at the full step (the fold is continuous),
+    // sgn * wz * h/2 at the half steps
+    const float dl = dbl ? __double2float_rn(th_fold - tg.thd) : tg.sgn * dth;
+    if (!dbl) {
+      // a half step may cross the fold: asin(sin x) = max(min(x, pi - x), -pi - x) for |x| < pi.  The pitch error feeds
+      // the derivative filter of the SS PID (gain Kd N ~ 390), so a kink missed for one pass would show in U_com_PID
+      const float x = tg.thf + dl;
+      thf = fmaxf(fminf(x, 3.14159274f - x), -3.14159274f - x);
+    }
+    const float d2 = dl * dl;
+    const float sd = fmaf(dl * d2, fmaf(d2, 8.33333333e-3f, -0.166666667f), dl);
+    const float cd = fmaf(d2, fmaf(d2, 4.16666667e-2f, -0.5f), 1.0f);
+    sn = fmaf(tg.sn, cd, tg.cs * sd);
+    cs = fabsf(fmaf(tg.cs, cd, -tg.sn * sd));  // the folded pitch stays within +-90 deg: cos >= 0 (a half step may cross the fold)
   }
   o.th = thf;
   o.thd = th_fold;
@@ -273,7 +292,16 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   const float V2 = fmaf(ub, ub, wb * wb);
   const float rV = rsqrt_fast(V2);
   const float V = V2 * rV;
-  const float alpha = alpha_of(wb, ub);
+  float alpha;
+  if (major) {
+    alpha = alpha_of(wb, ub);
+    tg.ub = ub; tg.wb = wb; tg.rV = rV; tg.alpha = alpha;
+  } else {
+    // alpha = angle of (ub, -wb): sin(alpha - alpha0) = (wb0 ub - ub0 wb) / (V0 V), asin by its series (|x| <~ 0.1)
+    const float x = fmaf(tg.wb, ub, -(tg.ub * wb)) * (tg.rV * rV);
+    const float x2 = x * x;
+    alpha = tg.alpha + fmaf(x * x2, fmaf(x2, 0.075f, 0.166666667f), x);
+  }
   o.V = V; o.alpha = alpha;
   // ISA atmosphere: density rho0 (T/T0)^(g/(LR)-1) [* exp(g/R sat(11000-h)/T) above the tropopause] and 1/a
   float rho, ia;
@@ -417,7 +445,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
               y_wz = __double2float_rn(r.wz), y_ssi = __double2float_rn(r.ssi), y_ssf = __double2float_rn(r.ssf),
               y_th = __double2float_rn(r.th);
   const float vref_f = __double2float_rn(r.vartheta);
-  float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf, Xf_th = y_th;
+  float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf, d_th = 0.f;
   double X_th = r.th, Xd_h = r.h, X_csi = r.csi, X_csf = r.csf;
   float a_h = 0, a_Vx = 0, a_Vy = 0, a_wz = 0, a_ssi = 0, a_ssf = 0, a_th = 0, a_x = 0;
   float a_dvi = 0, a_itse = 0;
@@ -425,6 +453,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
   bool memout_ss = false, memout_cs = false;
   float u_n = 0.f;
   AtmoMx at;
+  TrigMx tg;
 #if B747_UNROLL_STAGES
 #pragma unroll
 #else
@@ -435,7 +464,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
     const float t_f = s == 0 ? t0f : (s == 3 ? t0f + hh : t0f + hhalf);
     float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_itse;
     double f_csi, f_csf;
-    pass32<GEN>(sT, mp, c, s, n, X_th, Xf_th, vref_f, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, at,
+    pass32<GEN>(sT, mp, c, s, n, X_th, d_th, tg, vref_f, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, at,
                 memout_ss, memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
     if (s == 0) {
       // update(): discrete filter, rate-limiter memory, Memory blocks, Derivative history, delay push
@@ -464,7 +493,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
         s4.x = want_x ? (float)r.x + hh * X_Vx : 0.f;
         X_th = fma(kH, (double)X_wz, r.th);  // theta' = wz: the full-step pass needs the float64 pitch
       } else {
-        Xf_th = fmaf(cf, X_wz, y_th);        // half-step passes: float32 pitch
+        d_th = cf * X_wz;                    // half-step passes: float32 pitch increment since the major pass
       }
       X_h = fmaf(cf, f_h, y_h); X_Vx = fmaf(cf, f_Vx, y_Vx); X_Vy = fmaf(cf, f_Vy, y_Vy); X_wz = fmaf(cf, f_wz, y_wz);
       X_ssi = fmaf(cf, f_ssi, y_ssi); X_ssf = fmaf(cf, f_ssf, y_ssf);
