@@ -24,6 +24,7 @@ namespace b747 {
 enum { DG_h_th = 0, DG_V, DG_wz_ssi, DG_ssf_dvi, DG_itse_d1, DG_vref_ret, DG_cs, DG_x_href, DG_osc0, DG_osc1, DG_osc2,
        DG_s0a, DG_s0b, DG_s0c, ND_GROUPS };
 enum { FG_act = 0, FG_uh, FG_misc, FG_sumA, FG_misc2, NF_GROUPS };
+static_assert(DG_vref_ret == 5 && FG_misc == 2, "stage_issue copies D groups 0-5 and F groups 0-2");
 
 template <bool GEN>
 __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, RegsMx& r) {
@@ -60,6 +61,70 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
   }
   r.vartheta = 0.0;
   r.tc = TabCache{};  // look-up cache: zero widths = nothing cached, refilled on first use
+  r.tc.ix = 0xffffffffu;
+}
+
+// ---- TMA staging of the canonical (LEAN) state: each warp owns a 4.5 KB shared-memory buffer; one elected lane issues
+// nine 512-byte bulk copies (one per 16-byte field group of the warp's 32 environments) that complete on the warp's
+// mbarrier.  The copy of tile k+1 is issued as soon as tile k has been read into registers, so the HBM latency of the
+// next tile hides behind the K model steps of the current one and the memory system always has every warp's next
+// tile in flight (ncu r1e: at K = 1 the step was latency-bound at 58 % of the HBM roof with plain loads).
+#ifndef B747_STAGED
+#define B747_STAGED 0  // measured round 1: no gain over plain 128-bit loads (K=1: 0.091 vs 0.087 ms; K=10: 0.352 vs 0.344 ms)
+#endif
+constexpr int kStageGroups = 9, kStageBytes = kStageGroups * 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one lane: queue the nine field groups of the 32 environments starting at env i0
+__device__ __forceinline__ void stage_issue(const StateF32& st, size_t np, int i0, uint32_t buf, uint32_t bar) {
+  mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+  for (int g = 0; g < 6; g++) bulk_g2s(buf + g * 512, st.D + (size_t)g * np + i0, 512, bar);
+#pragma unroll
+  for (int g = 0; g < 3; g++) bulk_g2s(buf + (6 + g) * 512, st.F + (size_t)g * np + i0, 512, bar);
+}
+// all lanes: the staged copy of load_mx<false>
+__device__ __forceinline__ void load_mx_staged(const unsigned char* buf, int lane, RegsMx& r) {
+  const double2* D = (const double2*)buf;
+  const float4* F = (const float4*)(buf + 6 * 512);
+  double2 d;
+  d = D[DG_h_th * 32 + lane]; r.h = d.x; r.th = d.y;
+  d = D[DG_V * 32 + lane]; r.Vx = d.x; r.Vy = d.y;
+  d = D[DG_wz_ssi * 32 + lane]; r.wz = d.x; r.ssi = d.y;
+  d = D[DG_ssf_dvi * 32 + lane]; r.ssf = d.x; r.dvi = d.y;
+  d = D[DG_itse_d1 * 32 + lane]; r.itse = d.x; r.d1_u = d.y;
+  d = D[DG_vref_ret * 32 + lane]; r.vref = d.x; r.ep_return = d.y;
+  float4 f;
+  f = F[FG_act * 32 + lane]; r.df_x = f.x; r.df_y = f.y; r.rl_prev = f.z; r.deltaz = f.w;
+  f = F[FG_uh * 32 + lane]; r.uh[0] = f.x; r.uh[1] = f.y; r.uh[2] = f.z; r.uh[3] = f.w;
+  f = F[FG_misc * 32 + lane]; r.sig_upid = f.x; r.d2_u = f.y; r.tick = __float_as_int(f.z);
+  const unsigned fw = __float_as_uint(f.w);
+  r.flags = (int)(fw & 0xffu); r.ep_idx = fw >> 8;
+  r.csi = r.csf = r.x = 0.0; r.href = B747_DEF_H_ZH;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { r.oscA[k] = 0.0; r.oscf[k] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 5; k++) r.sumA[k] = 1.0f;
+  r.tf_tp = 0.f; r.sig_vzh = 0.f;
+  r.vartheta = 0.0;
+  r.tc = TabCache{};
   r.tc.ix = 0xffffffffu;
 }
 
@@ -157,23 +222,51 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
   // Persistent warps: the launch fills the GPU once (blocks = SMs x resident blocks per SM), the tables are staged into
   // shared memory once per block, and every warp then walks its own stride of 32-env tiles with no block-level
   // synchronisation until the episode statistics are flushed at the very end.
+  constexpr bool STAGED = !GEN && B747_STAGED;
   __shared__ float4 sT[kFastCells];
   __shared__ double s_stats[4];
-  if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
-  load_tables32(sT, st.tables);
+  __shared__ __align__(128) unsigned char sStage[STAGED ? 4 : 1][STAGED ? kStageBytes : 16];
+  __shared__ __align__(8) unsigned long long sBar[4];
   const size_t np = (size_t)c.n_pad;
-  const int lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
   const int n_tiles = (c.env_hi - c.env_lo + 31) >> 5;
+  const int wt0 = blockIdx.x * warps_per_block + warp, wstride = gridDim.x * warps_per_block;
+  const uint32_t bar = smem_u32(&sBar[warp]), buf = smem_u32(&sStage[STAGED ? warp : 0][0]);
+  if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
+  if (STAGED && lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (wt0 < n_tiles) stage_issue(st, np, c.env_lo + wt0 * 32, buf, bar);  // first tile: flies while the tables load
+  }
+  load_tables32(sT, st.tables);
+  uint32_t phase = 0;
+  float a_next = 0.f;
+  if (STAGED && wt0 < n_tiles && c.env_lo + wt0 * 32 + lane < c.env_hi) a_next = actions[c.env_lo + wt0 * 32 + lane];
 #pragma unroll 1
-  for (int wt = blockIdx.x * warps_per_block + (threadIdx.x >> 5); wt < n_tiles; wt += gridDim.x * warps_per_block) {
+  for (int wt = wt0; wt < n_tiles; wt += wstride) {
   const int i = c.env_lo + wt * 32 + lane;
   const bool live = i < c.env_hi;
   bool done = false;
   double ep_ret = 0.0, ep_len = 0.0;
+  RegsMx r;
+  float a = a_next;
+  if (STAGED) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    load_mx_staged(&sStage[STAGED ? warp : 0][0], lane, r);
+    __syncwarp();  // every lane has read its slots: the buffer can take the next tile
+    const int wn = wt + wstride;
+    if (wn < n_tiles) {
+      if (lane == 0) stage_issue(st, np, c.env_lo + wn * 32, buf, bar);
+      if (c.env_lo + wn * 32 + lane < c.env_hi) a_next = actions[c.env_lo + wn * 32 + lane];
+    }
+  }
   if (live) {
-    RegsMx r;
-    load_mx<GEN>(st, np, i, r);
-    float a = actions[i];
+    if (!STAGED) {
+      load_mx<GEN>(st, np, i, r);
+      a = actions[i];
+    }
     if (c.norm_act) a *= (float)c.action_max;
     const bool use_ctrl = GEN && (r.flags & FL_USE_CTRL);
     // Controller.step: reference, then the action law (core/controller.py:233-251)
@@ -222,9 +315,12 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
     // Controller.vartheta_ref (core/controller.py:267-270)
     const float vr = use_ctrl ? r.sig_vzh : (float)r.vartheta;
     // observation (env/ctrl_env.py:200-247)
-    float obs[10];
-    int od = c.obs_dim;
-    {
+    float obs[GEN ? 10 : 3];
+    const int od = GEN ? c.obs_dim : 3;
+    if (!GEN) {  // canonical layout (PID_LIKE): three scalars, no indexed array
+      obs[0] = (float)s4.dvi; obs[1] = dv; obs[2] = dv_dt_f;
+      if (c.norm_obs) { obs[0] /= (float)(60 * kPi); obs[1] /= (float)kPi; obs[2] /= (float)kPi; }
+    } else {
       const float pi = (float)kPi;
       if (c.obs_type == B747_OBS_MODEL_STATE) {
         obs[0] = vr; obs[1] = nan_to_num_f(s4.x); obs[2] = nan_to_num_f(s4.h); obs[3] = nan_to_num_f(s4.Vx);
@@ -295,7 +391,7 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
     done = (int64_t)r.tick >= c.done_tick;
     if (c.use_limiter && (fabsf(nan_to_num_f(o.th)) > (float)(5 * kPi / 180 + c.vartheta_max) || r.deltaz > (float)c.action_max))
       done = true;
-    if (st.sig) {
+    if (GEN && st.sig) {  // signal export: general kernel only (f32_is_lean)
       float* sg = st.sig;
 #define SG(name, v) sg[(size_t)SIG_##name * np + i] = (v)
       const float qn = nanf("");
@@ -325,7 +421,7 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
         env_reset_mx<GEN>(c, ep, r, st, np, i);
         full_store = true;
         for (int k = 0; k < od; k++) obs[k] = 0.f;
-        if (st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
+        if (GEN && st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
       }
     }
     if (od == 3) {  // canonical layout: three contiguous floats per env
@@ -394,7 +490,7 @@ __global__ void __launch_bounds__(128) k_defaults32(DevCfg c, StateF32 st) {
 // ---- host side --------------------------------------------------------------------------------
 bool f32_is_lean(const DevCfg& c) {
   return c.ctrl_type == B747_CTRL_MANUAL && c.reset_ref_mode == B747_RESET_CONST && c.disturbance_mode == B747_DIST_NONE &&
-         c.rew_type != B747_REW_TF_REFERENCE && c.obs_type != B747_OBS_MODEL_STATE;
+         c.rew_type != B747_REW_TF_REFERENCE && c.obs_type == B747_OBS_PID_LIKE;
 }
 
 static MP32 make_mp32(const ModelParams& m) {
@@ -461,7 +557,7 @@ void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions
   const MP32 mp = make_mp32(c.mp);
   const int n = c.env_hi - c.env_lo;
   if (n <= 0) return;
-  if (f32_is_lean(c) && !st.trace.trk && !st.trace.rec)
+  if (f32_is_lean(c) && !st.trace.trk && !st.trace.rec && !st.sig)
     k_env_step32<false><<<step_grid<false>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else
     k_env_step32<true><<<step_grid<true>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);

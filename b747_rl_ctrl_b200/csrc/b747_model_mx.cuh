@@ -151,7 +151,7 @@ __device__ __forceinline__ float4 axis_seek(const float4* __restrict__ sT, float
   }
   return q;
 }
-// first search of a launch: coarse index map of axis k (b747_tables.h), `lo`/`inv` = sentinel range of the axis
+// first search of a launch: coarse index map of axis k (b747_tables.h), `lo`/`inv` = range the map resolves
 template <int K>
 __device__ __forceinline__ int axis_guess(const float4* __restrict__ sT, float u, float lo, float inv) {
   const int b = min(max((int)((u - lo) * inv), 0), ft::LUT_N - 1);
@@ -178,9 +178,9 @@ __device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float
   const bool empty = ix == 0xffffffffu;
   constexpr float rad = (float)Pc(21);
   if (empty) {
-    iM = axis_guess<0>(sT, Mach, 0.f, (float)(ft::LUT_N / ft::EXT_M_HI));
-    iA = axis_guess<1>(sT, alpha, (float)(ft::EXT_A_LO / rad), (float)(ft::LUT_N * rad / (ft::EXT_A_HI - ft::EXT_A_LO)));
-    iH = axis_guess<2>(sT, h, (float)ft::EXT_H_LO, (float)(ft::LUT_N / (ft::EXT_H_HI - ft::EXT_H_LO)));
+    iM = axis_guess<0>(sT, Mach, (float)ft::LUT_M_LO, (float)(ft::LUT_N / (ft::LUT_M_HI - ft::LUT_M_LO)));
+    iA = axis_guess<1>(sT, alpha, (float)(ft::LUT_A_LO / rad), (float)(ft::LUT_N * rad / (ft::LUT_A_HI - ft::LUT_A_LO)));
+    iH = axis_guess<2>(sT, h, (float)ft::LUT_H_LO, (float)(ft::LUT_N / (ft::LUT_H_HI - ft::LUT_H_LO)));
   }
   TabMAH t;
   const float4 qM = axis_seek<ft::AXM, ft::NM>(sT, Mach, iM);
@@ -192,7 +192,7 @@ __device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float
   t.cDC = sT[ft::T_HM + iM * ft::NH + iH];
   if (empty) {
     const float CYa = bilinear(t.cCY, Mach - t.bM, alpha - t.bA) * cy_gain;
-    iC = axis_guess<3>(sT, CYa, (float)ft::EXT_C_LO, (float)(ft::LUT_N / (ft::EXT_C_HI - ft::EXT_C_LO)));
+    iC = axis_guess<3>(sT, CYa, (float)ft::LUT_C_LO, (float)(ft::LUT_N / (ft::LUT_C_HI - ft::LUT_C_LO)));
   }
   t.ix = (uint32_t)iM | (uint32_t)iA << 8 | (uint32_t)iH << 16 | (uint32_t)iC << 24;
   *out = t;

@@ -27,7 +27,7 @@
 //                                         on the alpha axis, 0 elsewhere.  The alpha axis is in radians.
 //   2-D cell (i0 along axis 0, i1 axis 1): {c0, c1, c2, c3}
 //   CYa and mz share both axes; their cells are interleaved (2 float4 per cell).
-//   coarse index map per axis: LUT_N bytes, bucket b of the sentinel range -> interval holding the bucket's lower
+//   coarse index map per axis: LUT_N bytes, bucket b of the flight-envelope range -> interval holding the bucket's lower
 //                                         edge; the first search of a launch starts there (the kernel then walks 0..2 steps)
 // Host-only code (no CUDA types); the device side reads it through the offsets below.
 #pragma once
@@ -53,6 +53,9 @@ constexpr int CELLS = LUT + 4 * LUT_N / 16;  // 1216 float4 = 19456 bytes
 // sentinel breakpoints (alpha in degrees, like the DLL's tables)
 constexpr double EXT_M_HI = 2.0, EXT_A_LO = -40.0, EXT_A_HI = 75.0, EXT_H_LO = -4000.0, EXT_H_HI = 24000.0, EXT_C_LO = -4.0,
                  EXT_C_HI = 4.0;
+// ranges the coarse index maps resolve (flight envelope; operands outside start from the end bucket and walk)
+constexpr double LUT_M_LO = 0.0, LUT_M_HI = 1.0, LUT_A_LO = -10.0, LUT_A_HI = 35.0, LUT_H_LO = -4000.0, LUT_H_HI = 24000.0,
+                 LUT_C_LO = -0.4, LUT_C_HI = 1.6;
 
 // ---- float64 restatement of the DLL's interpolation (test oracle for the re-gridding) ----
 inline void prelook(double u, const double* bp, int maxIndex, int& idx, double& frac) {
@@ -156,17 +159,18 @@ inline Fast build() {
       cell(q + 4, O.mz(F.bM[iM], F.bA[iA]), O.mz(F.bM[iM + 1], F.bA[iA]), O.mz(F.bM[iM], F.bA[iA + 1]),
            O.mz(F.bM[iM + 1], F.bA[iA + 1]), wd(F.bM, iM, 1.0), wd(F.bA, iA, rad));
     }
-  auto lut = [&](int k, const std::vector<double>& b) {
+  auto lut = [&](int k, const std::vector<double>& b, double lo, double hi) {
     unsigned char* L = reinterpret_cast<unsigned char*>(&F.v[(size_t)LUT * 4]) + k * LUT_N;
     const int n = (int)b.size() - 1;
     for (int j = 0; j < LUT_N; j++) {
-      const double u = b.front() + (b.back() - b.front()) * j / LUT_N;
+      const double u = lo + (hi - lo) * j / LUT_N;
       int i = 0;
       while (i < n - 1 && u >= b[i + 1]) i++;
       L[j] = (unsigned char)i;
     }
   };
-  lut(0, F.bM); lut(1, F.bA); lut(2, F.bH); lut(3, F.bC);
+  lut(0, F.bM, LUT_M_LO, LUT_M_HI); lut(1, F.bA, LUT_A_LO, LUT_A_HI); lut(2, F.bH, LUT_H_LO, LUT_H_HI);
+  lut(3, F.bC, LUT_C_LO, LUT_C_HI);
   F.ok = true;
   return F;
 }
