@@ -34,10 +34,15 @@ struct b747_handle {
   void *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_term = nullptr;
   uint8_t* d_done = nullptr;
   // b747_step_host pipeline: copy-in / second compute / copy-out streams and per-chunk events (created on first use)
-  cudaStream_t s_in = nullptr, s_aux = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_aux = nullptr, s_out = nullptr, s_cap = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_k;
-  cudaEvent_t ev_start = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_done = nullptr;
   int host_chunks = 0;  // 0 = choose from n_envs
+  // the pipeline as an instantiated CUDA graph per set of (pinned) host buffers: one launch call per env step
+  struct HostGraph { const void* act; void *obs, *rew, *done, *term; int chunks; uint64_t epoch; cudaGraphExec_t exec; };
+  std::vector<HostGraph> graphs;
+  uint64_t epoch = 0;     // bumped by everything that changes launch arguments (b747_set_param)
+  bool use_graphs = true;
   b747_episode* d_eps = nullptr;
   double* d_metrics = nullptr;  // [n_pad][5] staging for b747_transfer_metrics
   TraceState trace;
@@ -222,6 +227,7 @@ extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
     if (rc) return fail(B747_ERR_CUDA, std::string("f32 state allocation: ") + cudaGetErrorString(cudaGetLastError()));
     launch_defaults32(h->dc, h->s32, h->stream);
     h->launches++;
+    f32_warm_launch();
   }
   CU(cudaMalloc(&h->d_act, h->elem() * np));
   CU(cudaMalloc(&h->d_obs, h->elem() * np * od));
@@ -249,9 +255,12 @@ extern "C" int b747_destroy(b747_handle* h) {
   for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_k) cudaEventDestroy(e);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_aux) cudaStreamDestroy(h->s_aux);
   if (h->s_out) cudaStreamDestroy(h->s_out);
+  if (h->s_cap) cudaStreamDestroy(h->s_cap);
   delete h;
   return B747_OK;
 }
@@ -369,6 +378,44 @@ extern "C" int b747_set_host_chunks(b747_handle* h, int n_chunks) {
   return B747_OK;
 }
 
+// Enqueue one pipelined env step: forks from the handle's stream (copy-in, second compute and copy-out streams) and joins
+// back into it, so the whole step is ordered like a single operation on that stream -- and can be stream-captured.
+static int issue_pipeline(b747_handle* h, cudaStream_t origin, const void* act, void* obs, void* rew, uint8_t* done,
+                          void* term, int chunks, size_t per) {
+  const size_t n = (size_t)h->cfg.n_envs, es = h->elem(), od = (size_t)h->dc.obs_dim;
+  // everything queued on the handle's stream so far (resets, device-side steps) comes first
+  CU(cudaEventRecord(h->ev_start, origin));
+  CU(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+  CU(cudaStreamWaitEvent(h->s_aux, h->ev_start, 0));
+  const char* a8 = (const char*)act;
+  char *o8 = (char*)obs, *r8 = (char*)rew, *t8 = (char*)term;
+  for (int c = 0; c < chunks; c++) {
+    const size_t lo = (size_t)c * per, hi = std::min(n, lo + per), m = hi - lo;
+    CU(cudaMemcpyAsync((char*)h->d_act + es * lo, a8 + es * lo, es * m, cudaMemcpyHostToDevice, h->s_in));
+    CU(cudaEventRecord(h->ev_in[c], h->s_in));
+    cudaStream_t sc = (c & 1) ? h->s_aux : origin;
+    CU(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
+    step_chunk(h, (int)lo, (int)hi, term != nullptr, sc);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_k[c], sc));
+    CU(cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+    CU(cudaMemcpyAsync(o8 + es * od * lo, (char*)h->d_obs + es * od * lo, es * od * m, cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaMemcpyAsync(r8 + es * lo, (char*)h->d_rew + es * lo, es * m, cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaMemcpyAsync(done + lo, h->d_done + lo, m, cudaMemcpyDeviceToHost, h->s_out));
+    if (term) CU(cudaMemcpyAsync(t8 + es * od * lo, (char*)h->d_term + es * od * lo, es * od * m, cudaMemcpyDeviceToHost, h->s_out));
+  }
+  // join: the copy-out stream has seen every chunk's kernel (and through them every copy-in)
+  CU(cudaEventRecord(h->ev_done, h->s_out));
+  CU(cudaStreamWaitEvent(origin, h->ev_done, 0));
+  return B747_OK;
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int b747_step_host(b747_handle* h, const void* act, void* obs, void* rew, uint8_t* done, void* term) {
   if (!h || !act || !obs || !rew || !done) return fail(B747_ERR_ARG, "null argument");
   if (!h->cfg.env_layer) return fail(B747_ERR_STATE, "handle was created with env_layer=0; use b747_model_step");
@@ -392,7 +439,9 @@ extern "C" int b747_step_host(b747_handle* h, const void* act, void* obs, void* 
     CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   }
   while ((int)h->ev_in.size() < chunks) {
     cudaEvent_t a, b;
@@ -400,30 +449,45 @@ extern "C" int b747_step_host(b747_handle* h, const void* act, void* obs, void* 
     CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     h->ev_in.push_back(a); h->ev_k.push_back(b);
   }
-  // everything queued on the handle's stream so far (resets, device-side steps) comes first
-  CU(cudaEventRecord(h->ev_start, h->stream));
-  CU(cudaStreamWaitEvent(h->s_aux, h->ev_start, 0));
-  const char* a8 = (const char*)act;
-  char *o8 = (char*)obs, *r8 = (char*)rew, *t8 = (char*)term;
-  for (int c = 0; c < chunks; c++) {
-    const size_t lo = (size_t)c * per, hi = std::min(n, lo + per), m = hi - lo;
-    CU(cudaMemcpyAsync((char*)h->d_act + es * lo, a8 + es * lo, es * m, cudaMemcpyHostToDevice, h->s_in));
-    CU(cudaEventRecord(h->ev_in[c], h->s_in));
-    cudaStream_t sc = (c & 1) ? h->s_aux : h->stream;
-    CU(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
-    step_chunk(h, (int)lo, (int)hi, term != nullptr, sc);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(h->ev_k[c], sc));
-    CU(cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
-    CU(cudaMemcpyAsync(o8 + es * od * lo, (char*)h->d_obs + es * od * lo, es * od * m, cudaMemcpyDeviceToHost, h->s_out));
-    CU(cudaMemcpyAsync(r8 + es * lo, (char*)h->d_rew + es * lo, es * m, cudaMemcpyDeviceToHost, h->s_out));
-    CU(cudaMemcpyAsync(done + lo, h->d_done + lo, m, cudaMemcpyDeviceToHost, h->s_out));
-    if (term) CU(cudaMemcpyAsync(t8 + es * od * lo, (char*)h->d_term + es * od * lo, es * od * m, cudaMemcpyDeviceToHost, h->s_out));
+  // Pinned buffers: the ~70 stream operations of the pipeline are captured once per buffer set into a CUDA graph and
+  // replayed with one launch call per step (the host-side issue time of the eager form is a third of the step).
+  if (h->use_graphs && is_pinned(act) && is_pinned(obs) && is_pinned(rew) && is_pinned(done) && (!term || is_pinned(term))) {
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : h->graphs)
+      if (g.act == act && g.obs == obs && g.rew == rew && g.done == done && g.term == term && g.chunks == chunks &&
+          g.epoch == h->epoch) { exec = g.exec; break; }
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      // captured on an internal stream (the handle's stream may be the legacy default stream, which cannot capture)
+      CU(cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal));
+      const int64_t launches0 = h->launches;
+      const int rc = issue_pipeline(h, h->s_cap, act, obs, rew, done, term, chunks, per);
+      h->launches = launches0;
+      const cudaError_t ce = cudaStreamEndCapture(h->s_cap, &graph);
+      if (rc != B747_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->use_graphs = false;  // capture is not available here: eager pipeline from now on
+      } else {
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); exec = nullptr; h->use_graphs = false; }
+        else {
+          if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+          h->graphs.push_back({act, obs, rew, (void*)done, term, chunks, h->epoch, exec});
+        }
+      }
+    }
+    if (exec) {
+      CU(cudaGraphLaunch(exec, h->stream));
+      h->launches += chunks;
+      CU(cudaStreamSynchronize(h->stream));
+      return B747_OK;
+    }
   }
-  // later work on the handle's stream is ordered after the odd chunks too
-  CU(cudaStreamWaitEvent(h->stream, h->ev_k[chunks - 1], 0));
-  if (chunks > 1) CU(cudaStreamWaitEvent(h->stream, h->ev_k[chunks - 2], 0));
-  CU(cudaStreamSynchronize(h->s_out));
+  const int rc = issue_pipeline(h, h->stream, act, obs, rew, done, term, chunks, per);
+  if (rc != B747_OK) return rc;
+  CU(cudaStreamSynchronize(h->stream));
   return B747_OK;
 }
 
@@ -469,6 +533,7 @@ extern "C" int b747_set_param(b747_handle* h, const char* name, const double* v,
   double* p = param_ptr(h->dc.mp, name, len);
   if (!p || n != len) return fail(B747_ERR_ARG, std::string("unknown parameter or wrong length: ") + name);
   memcpy(p, v, sizeof(double) * len);
+  h->epoch++;  // launch arguments changed: captured pipelines are stale
   return B747_OK;
 }
 extern "C" int b747_get_param(b747_handle* h, const char* name, double* v, int n) {

@@ -552,6 +552,9 @@ static int step_grid(int n) {
   return need < resident[dev] ? need : resident[dev];
 }
 
+// resolve the persistent grids once, outside any stream capture (b747_create)
+void f32_warm_launch() { step_grid<false>(1 << 30); step_grid<true>(1 << 30); }
+
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s) {
   const MP32 mp = make_mp32(c.mp);

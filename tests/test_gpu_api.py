@@ -232,6 +232,35 @@ def test_step_host_pipeline_equals_one_launch(dtype_name, n):
         e.close()
 
 
+def test_step_host_graph_replay_with_pinned_buffers():
+    """With pinned host buffers b747_step_host replays its pipeline as a CUDA graph (one launch call per step); results
+    equal the eager pipeline's on pageable buffers, across buffer sets and across a parameter change."""
+    import torch
+    from b747_rl_ctrl_b200 import engine as E
+    n = 3000
+    engs = [E.BatchEngine(n_envs=n, dtype=E.F32, seed=8, sample_time=0.05, tk=0.5) for _ in range(2)]
+    for e in engs:
+        e.set_host_chunks(4)
+        e.reset()
+    pin = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt).pin_memory()
+    acts = [pin(n) for _ in range(3)]
+    obs_p, rew_p, done_p = pin(n, 3), pin(n), pin(n, dt=torch.uint8)
+    rng = np.random.default_rng(2)
+    for k in range(24):
+        if k == 12:  # launch arguments change: the captured graphs must not be replayed
+            for e in engs:
+                e.set_param("P", [2.0e5])
+        a = rng.uniform(-1, 1, n).astype(np.float32)
+        o0, r0, d0 = engs[0].step_host(a)
+        buf = acts[k % 3]
+        buf.copy_(torch.from_numpy(a))
+        engs[1].step_host(buf.numpy(), obs_p.numpy(), rew_p.numpy(), done_p.numpy())
+        assert np.array_equal(o0, obs_p.numpy()) and np.array_equal(r0, rew_p.numpy()) and np.array_equal(d0, done_p.numpy()), k
+    assert engs[0].launch_count == engs[1].launch_count
+    for e in engs:
+        e.close()
+
+
 def test_ppo_learns_on_gpu_vecenv():
     """BASELINE configs[4] in miniature: PPO (SB3-default hyper-parameters restated in torch) on 8192 GPU environments
     improves the episode return well beyond the untrained policy within a few seconds."""
