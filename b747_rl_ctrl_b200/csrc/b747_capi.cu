@@ -333,6 +333,14 @@ extern "C" int b747_reset(b747_handle* h, const uint8_t* mask_dev, void* obs_dev
 extern "C" int b747_reset_to(b747_handle* h, const b747_episode* eps, void* obs_dev) {
   if (!h || !eps) return fail(B747_ERR_ARG, "null argument");
   CU(cudaSetDevice(h->cfg.device));
+  // explicit episodes can ask for what the handle's configuration family never produces (closed altitude loop,
+  // oscillating reference, aero errors): from then on the f32 launch takes the full kernel tier
+  for (int i = 0; i < h->cfg.n_envs && !h->dc.force_full; i++) {
+    const b747_episode& e = eps[i];
+    bool special = e.use_ctrl || e.oscillating;
+    for (int k = 0; k < 5; k++) special = special || e.aero_err[k] != 0.0;
+    if (special) { h->dc.force_full = 1; h->epoch++; }
+  }
   CU(cudaMemcpyAsync(h->d_eps, eps, sizeof(b747_episode) * h->cfg.n_envs, cudaMemcpyHostToDevice, h->stream));
   if (h->cfg.dtype == B747_F64) launch_reset64(h->dc, h->s64, nullptr, h->d_eps, (double*)obs_dev, h->stream);
   else launch_reset32(h->dc, h->s32, nullptr, h->d_eps, (float*)obs_dev, h->stream);
@@ -592,6 +600,7 @@ extern "C" int b747_get_field(b747_handle* h, int field, double* out) {
 }
 extern "C" int b747_set_field(b747_handle* h, int field, const double* in) {
   if (!in) return fail(B747_ERR_ARG, "null argument");
+  if (h && field == b747_field_index("flags") && !h->dc.force_full) { h->dc.force_full = 1; h->epoch++; }
   return field_io(h, field, nullptr, in);
 }
 

@@ -76,6 +76,7 @@ struct DevCfg {
   int32_t env_lo, env_hi;  // env range of this launch of the step kernels ([0, n_envs) except in b747_step_host's pipeline)
   int32_t obs_type, obs_dim, rew_type, ctrl_type, ctrl_mode, reset_ref_mode, disturbance_mode;
   int32_t norm_obs, norm_act, use_limiter, substeps, auto_reset, env_layer, has_fixed_aero_err;
+  int32_t force_full;  // explicit episodes / edited flags: the f32 launch must take the full kernel tier
   int64_t done_tick, env_id_offset;
   uint64_t seed;
   double tk, action_max, vartheta_max, sample_time;

@@ -36,6 +36,7 @@ struct StateF32 {
 int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t stream);
 void f32_free(StateF32& s);
 bool f32_is_lean(const DevCfg& c);
+bool f32_needs_cs(const DevCfg& c);
 void f32_warm_launch();
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s);

@@ -215,13 +215,22 @@ __device__ __forceinline__ void load_tables32(float4* sT, const float4* __restri
 #ifndef B747_F32_MINBLOCKS
 #define B747_F32_MINBLOCKS 4
 #endif
-template <bool GEN>
-__global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
+#ifndef B747_EXT_MINBLOCKS
+#define B747_EXT_MINBLOCKS 3
+#endif
+#ifndef B747_GEN_MINBLOCKS
+#define B747_GEN_MINBLOCKS 3  // measured: 168 registers x 12 warps beats 242 x 8 (0.66 -> 0.52 ms per 1 Mi-env K=10 step)
+#endif
+// TIER 0: canonical family (LEAN layout); 1: general layout without the altitude loop (other observation layouts,
+// oscillating references, aero disturbance, TF reward, signal export, trace); 2: + the altitude loop (СУ PID).
+template <int TIER>
+__global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER == 1 ? B747_EXT_MINBLOCKS : B747_F32_MINBLOCKS)) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                     uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
   // Persistent warps: the launch fills the GPU once (blocks = SMs x resident blocks per SM), the tables are staged into
   // shared memory once per block, and every warp then walks its own stride of 32-env tiles with no block-level
   // synchronisation until the episode statistics are flushed at the very end.
+  constexpr bool GEN = TIER >= 1, CS = TIER >= 2;
   constexpr bool STAGED = !GEN && B747_STAGED;
   __shared__ float4 sT[kFastCells];
   __shared__ double s_stats[4];
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
       a = actions[i];
     }
     if (c.norm_act) a *= (float)c.action_max;
-    const bool use_ctrl = GEN && (r.flags & FL_USE_CTRL);
+    const bool use_ctrl = CS && (r.flags & FL_USE_CTRL);
     // Controller.step: reference, then the action law (core/controller.py:233-251)
     if (!use_ctrl) {
       if (GEN && (r.flags & FL_OSC)) {
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(128, GEN ? 2 : B747_F32_MINBLOCKS) k_env_step3
     const bool want_x = GEN && (c.obs_type == B747_OBS_MODEL_STATE || tracing);
 #pragma unroll 1
     for (int k = 0; k < c.substeps; k++) {
-      model_step32<GEN>(sT, mp, c, r, o, s4, want_x);
+      model_step32<TIER>(sT, mp, c, r, o, s4, want_x);
       if (GEN && tracing) {  // Controller._post_step (core/controller.py:209-228)
         TraceSample ts;
         ts.t = (double)r.tick * kH; ts.U_com = o.U_com; ts.U_PID = o.U_com_PID; ts.deltaz_RP = o.deltaz_RP;
@@ -493,6 +502,12 @@ bool f32_is_lean(const DevCfg& c) {
          c.rew_type != B747_REW_TF_REFERENCE && c.obs_type == B747_OBS_PID_LIKE;
 }
 
+// can the altitude loop be closed (FL_USE_CTRL set by a reset)?  Explicit episodes (b747_reset_to) and flag edits set
+// DevCfg::force_full instead.
+bool f32_needs_cs(const DevCfg& c) {
+  return c.ctrl_type != B747_CTRL_MANUAL || c.reset_ref_mode == B747_RESET_HYBRID || c.reset_ref_mode == B747_RESET_NONE;
+}
+
 static MP32 make_mp32(const ModelParams& m) {
   MP32 p;
   for (int k = 0; k < 4; k++) p.PID_SS[k] = (float)m.PID_SS[k];
@@ -535,7 +550,7 @@ static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 #define B747_PERSISTENT 1  // 0: one 128-env tile per block (grid = all tiles)
 #endif
 // grid of the step kernel: enough blocks to fill every SM at the kernel's occupancy, never more than the tiles need
-template <bool GEN>
+template <int TIER>
 static int step_grid(int n) {
   const int need = grid_for(n, 128);
   if (!B747_PERSISTENT) return need;
@@ -546,24 +561,27 @@ static int step_grid(int n) {
   if (!resident[dev]) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step32<GEN>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step32<TIER>, 128, 0);
     resident[dev] = sms > 0 && per_sm > 0 ? sms * per_sm : need;
   }
   return need < resident[dev] ? need : resident[dev];
 }
 
 // resolve the persistent grids once, outside any stream capture (b747_create)
-void f32_warm_launch() { step_grid<false>(1 << 30); step_grid<true>(1 << 30); }
+void f32_warm_launch() { step_grid<0>(1 << 30); step_grid<1>(1 << 30); step_grid<2>(1 << 30); }
 
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s) {
   const MP32 mp = make_mp32(c.mp);
   const int n = c.env_hi - c.env_lo;
   if (n <= 0) return;
-  if (f32_is_lean(c) && !st.trace.trk && !st.trace.rec && !st.sig)
-    k_env_step32<false><<<step_grid<false>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+  const bool plain = !st.trace.trk && !st.trace.rec && !st.sig && !c.force_full;
+  if (plain && f32_is_lean(c))
+    k_env_step32<0><<<step_grid<0>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+  else if (plain && !f32_needs_cs(c))
+    k_env_step32<1><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else
-    k_env_step32<true><<<step_grid<true>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    k_env_step32<2><<<step_grid<2>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
 }
 void launch_reset32(const DevCfg& c, const StateF32& st, const uint8_t* mask, const b747_episode* eps, float* obs,
                     cudaStream_t s) {

@@ -232,13 +232,15 @@ struct TrigMx { float sn, cs, thf, sgn, ub, wb, rV, alpha; double thd; };
 // One pass over the diagram at a stage state.  stage: 0 major, 1/2 half steps, 3 full step.
 // Passes 0 and 3 -- the ones whose pitch error is differenced by the Derivative blocks, observed and rewarded -- carry
 // the pitch angle and the pitch error in float64 (th_d); the half-step passes only feed float32 RK4 sums and use th_f.
-template <bool GEN>
+// TIER 0: canonical (LEAN) model; 1: + aero-disturbance gains (general layout, no altitude loop); 2: + the altitude loop (СУ PID)
+template <int TIER>
 __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, int stage, int n,
                                        double th_d, float dth, TrigMx& tg, float vref_f, float t_f, float h, double h_d, float Vx,
                                        float Vy, float wz, float ssi, float ssf, double csi, double csf, RegsMx& r,
                                        AtmoMx& at, bool& memout_ss, bool& memout_cs, PassMx& o, float& f_h, float& f_Vx,
                                        float& f_Vy, float& f_wz, float& f_ssi, float& f_ssf, double& f_csi, double& f_csf,
                                        float& f_itse) {
+  constexpr bool GEN = TIER >= 1, CS = TIER >= 2;
   const bool major = stage == 0;
   const bool dbl = stage == 0 || stage == 3;
   // attitude.  Beyond +-90 deg the DLL's pitch asin(sin(theta)) folds back: with k = round(theta/pi) and
@@ -378,7 +380,7 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   // altitude-error chain is float64 (a float32 altitude quantises it at ~1e-5 rad).
   bool use_cs = false;
   double cs_pre = 0.0, cs_d = 0.0, e_h = 0.0, vzh_d = 0.0;
-  if (GEN) {
+  if (CS) {
     use_cs = (r.flags & FL_USE_CTRL) && (1.f >= PCF(146));
     e_h = r.href - h_d;  // h_zh - h
     cs_d = (e_h * c.mp.PID_CS[2] - csf) * c.mp.PID_CS[3];
@@ -391,11 +393,11 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   // pitch error
   float dv;
   if (dbl) {
-    const double dv_d = ((GEN && use_cs) ? vzh_d : r.vartheta) - th_fold;
+    const double dv_d = ((CS && use_cs) ? vzh_d : r.vartheta) - th_fold;
     o.dv = dv_d;
     dv = __double2float_rn(dv_d);
   } else {
-    dv = ((GEN && use_cs) ? o.vartheta_zh : vref_f) - thf;
+    dv = ((CS && use_cs) ? o.vartheta_zh : vref_f) - thf;
   }
   o.dvf = dv;
   // СС PID
@@ -420,7 +422,7 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   if (memout_ss) ss_i = PCF(10);
   f_h = Vy; f_Vx = ax; f_Vy = ay; f_wz = wzd; f_ssi = ss_i; f_ssf = ss_d;
   f_itse = dv * dv * t_f;
-  if (GEN) {
+  if (CS) {
     const double dzc = cs_pre - vzh_d;
     double cs_i = e_h * c.mp.PID_CS[1];
     o.and_cs = (cs_pre * Pc(292) != dzc) && (((dzc > 0.0) - (dzc < 0.0)) == ((cs_i > 0.0) - (cs_i < 0.0)));
@@ -434,9 +436,10 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
 
 // model_simple_step in the mixed formulation.  On return r holds the post-update state, `o` the
 // stage-4 pass and s4 the stage-4 (predictor) state values.
-template <bool GEN>
+template <int TIER>
 __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, RegsMx& r,
                                              PassMx& o, Stage4Mx& s4, bool want_x) {
+  constexpr bool CS = TIER >= 2;
   const int n = r.tick;
   const float hh = (float)kH, hhalf = 0.5f * (float)kH;
   const float t0f = (float)n * hh;
@@ -464,7 +467,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
     const float t_f = s == 0 ? t0f : (s == 3 ? t0f + hh : t0f + hhalf);
     float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_itse;
     double f_csi, f_csf;
-    pass32<GEN>(sT, mp, c, s, n, X_th, d_th, tg, vref_f, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, at,
+    pass32<TIER>(sT, mp, c, s, n, X_th, d_th, tg, vref_f, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, at,
                 memout_ss, memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
     if (s == 0) {
       // update(): discrete filter, rate-limiter memory, Memory blocks, Derivative history, delay push
@@ -480,7 +483,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
     const double wd = ends ? 1.0 : 2.0;
     a_h = fmaf(w, f_h, a_h); a_Vx = fmaf(w, f_Vx, a_Vx); a_Vy = fmaf(w, f_Vy, a_Vy); a_wz = fmaf(w, f_wz, a_wz);
     a_ssi = fmaf(w, f_ssi, a_ssi); a_ssf = fmaf(w, f_ssf, a_ssf); a_th = fmaf(w, X_wz, a_th);
-    if (GEN) { a_csi = fma(wd, f_csi, a_csi); a_csf = fma(wd, f_csf, a_csf); }
+    if (CS) { a_csi = fma(wd, f_csi, a_csi); a_csf = fma(wd, f_csf, a_csf); }
     if (want_x) a_x = fmaf(w, X_Vx, a_x);
     a_dvi = fmaf(w, o.dvf, a_dvi);
     a_itse = fmaf(w, f_itse, a_itse);
@@ -497,7 +500,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
       }
       X_h = fmaf(cf, f_h, y_h); X_Vx = fmaf(cf, f_Vx, y_Vx); X_Vy = fmaf(cf, f_Vy, y_Vy); X_wz = fmaf(cf, f_wz, y_wz);
       X_ssi = fmaf(cf, f_ssi, y_ssi); X_ssf = fmaf(cf, f_ssf, y_ssf);
-      if (GEN) {
+      if (CS) {
         X_csi = fma(cfd, f_csi, r.csi); X_csf = fma(cfd, f_csf, r.csf);
         Xd_h = fma(cfd, (double)f_h, r.h);
       }
@@ -508,7 +511,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
   const double h6d = kH / 6.0;
   r.h += (double)(h6 * a_h); r.Vx += (double)(h6 * a_Vx); r.Vy += (double)(h6 * a_Vy); r.wz += (double)(h6 * a_wz);
   r.ssi += (double)(h6 * a_ssi); r.ssf += (double)(h6 * a_ssf); r.th += (double)(h6 * a_th);
-  if (GEN) { r.csi = fma(h6d, a_csi, r.csi); r.csf = fma(h6d, a_csf, r.csf); }
+  if (CS) { r.csi = fma(h6d, a_csi, r.csi); r.csf = fma(h6d, a_csf, r.csf); }
   if (want_x) r.x += (double)(h6 * a_x);
   r.dvi += (double)(h6 * a_dvi);
   r.itse += (double)(h6 * a_itse);

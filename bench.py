@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -308,9 +308,18 @@ def run_cuda(args, rank, local_rank, world):
             line["cpu_baseline"] = info
         except Exception as e:  # the CPU leg must never hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "error", "sample": repr(e)}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL banner ...) to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process (native libraries write to fd 1 directly)
 
 
 def main():
