@@ -179,7 +179,10 @@ __device__ __forceinline__ void load_tables64(double* sP) {
 // ------------------------------------------------------------------------------------------
 // ControllerEnv.step for every env of the handle.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_env_step64(DevCfg c, StateF64 st, const double* __restrict__ actions,
+#ifndef B747_F64_MINBLOCKS
+#define B747_F64_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, B747_F64_MINBLOCKS) k_env_step64(DevCfg c, StateF64 st, const double* __restrict__ actions,
                                                     double* __restrict__ obs_out, double* __restrict__ rew_out,
                                                     uint8_t* __restrict__ done_out, double* __restrict__ term_obs) {
   __shared__ double sP[kNP];

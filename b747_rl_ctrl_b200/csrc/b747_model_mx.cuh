@@ -65,7 +65,9 @@ constexpr int kFastCells = ft::CELLS;
 struct TabCache {
   float bM, wM, bA, wA, bH, wH, bC, wC;  // lower breakpoint and width of the current interval (alpha in radians)
   float k0, k1;                          // K_alpha = k0 + k1 dA on the current alpha interval
-  float4 cCY, cMZ, cCX, cDC;             // cells: y = (c.x + c.y d0) + (c.z + c.w d0) d1
+  // cells as coefficient PAIRS for packed FFMA2 evaluation, y = (c0 + c1 dM) + (c2 + c3 dM) d1 with d1 = dA / dC / dH:
+  float2 pCM[4];                         // (CYa, mz) coefficient pairs k = 0..3 (the two tables share both operands)
+  float2 cxA, cxB, dcA, dcB;             // CXa and dCm cells as (c3, c1) and (c2, c0): inner terms by one FFMA2
   uint32_t ix;                           // interval indices iM | iA << 8 | iH << 16 | iC << 24 (read by the refill only)
 };
 
@@ -161,6 +163,11 @@ __device__ __forceinline__ int axis_guess(const float4* __restrict__ sT, float u
 __device__ __forceinline__ float bilinear(const float4 c, float d0, float d1) {
   return fmaf(fmaf(c.w, d0, c.z), d1, fmaf(c.y, d0, c.x));
 }
+// two tables at once: three FFMA2 (sm_100 packed FP32; the scalar offsets ride as broadcast operands)
+__device__ __forceinline__ float2 bilinear2(const float2 p[4], float d0, float2 d1) {
+  const float2 d00 = make_float2(d0, d0);
+  return __ffma2_rn(__ffma2_rn(p[3], d00, p[2]), d1, __ffma2_rn(p[1], d00, p[0]));
+}
 
 // Cold paths.  An operand left its cached interval (or nothing is cached yet); interval indices move incrementally (an
 // operand crosses into a NEIGHBOUR interval).  The cached record of an axis is always the one `ix` names, so cells and
@@ -170,7 +177,7 @@ __device__ __forceinline__ float bilinear(const float4 c, float d0, float d1) {
 //    the fully inlined form doubled the loop to 26 KB and tripled the no_instruction stalls).
 //  * CYa miss -- the common case, CYa crosses its 0.1-wide intervals with every degree of alpha: a few inline
 //    instructions move the interval and reload the CXa cell.
-struct TabMAH { float bM, wM, bA, wA, bH, wH, k0, k1; float4 cCY, cMZ, cDC; uint32_t ix; };
+struct TabMAH { float bM, wM, bA, wA, bH, wH, k0, k1; float4 cm0, cm1, cDC; uint32_t ix; };
 
 __device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float Mach, float alpha, float h, float cy_gain,
                                             uint32_t ix, TabMAH* __restrict__ out) {
@@ -188,10 +195,10 @@ __device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float
   const float4 qH = axis_seek<ft::AXH, ft::NH>(sT, h, iH);
   t.bM = qM.x; t.wM = qM.y; t.bA = qA.x; t.wA = qA.y; t.k0 = qA.z; t.k1 = qA.w; t.bH = qH.x; t.wH = qH.y;
   const float4* cMA = sT + ft::T_MA + 2 * (iA * ft::NM + iM);
-  t.cCY = cMA[0]; t.cMZ = cMA[1];
+  t.cm0 = cMA[0]; t.cm1 = cMA[1];
   t.cDC = sT[ft::T_HM + iM * ft::NH + iH];
   if (empty) {
-    const float CYa = bilinear(t.cCY, Mach - t.bM, alpha - t.bA) * cy_gain;
+    const float CYa = bilinear(make_float4(t.cm0.x, t.cm0.z, t.cm1.x, t.cm1.z), Mach - t.bM, alpha - t.bA) * cy_gain;
     iC = axis_guess<3>(sT, CYa, (float)ft::LUT_C_LO, (float)(ft::LUT_N / (ft::LUT_C_HI - ft::LUT_C_LO)));
   }
   t.ix = (uint32_t)iM | (uint32_t)iA << 8 | (uint32_t)iH << 16 | (uint32_t)iC << 24;
@@ -199,20 +206,25 @@ __device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float
 }
 
 __device__ __forceinline__ void tab_update(const float4* __restrict__ sT, float Mach, float alpha, float h, float cy_gain,
-                                           bool missMAH, TabCache& t, float& dM, float& dA, float& dH, float& CYa, float& dC) {
+                                           bool missMAH, TabCache& t, float& dM, float& dA, float& dH, float2& cm, float& dC) {
   if (missMAH) {
     TabMAH m;
     tab_refill_mah(sT, Mach, alpha, h, cy_gain, t.ix, &m);
     t.bM = m.bM; t.wM = m.wM; t.bA = m.bA; t.wA = m.wA; t.bH = m.bH; t.wH = m.wH; t.k0 = m.k0; t.k1 = m.k1;
-    t.cCY = m.cCY; t.cMZ = m.cMZ; t.cDC = m.cDC; t.ix = m.ix;
+    t.pCM[0] = make_float2(m.cm0.x, m.cm0.y); t.pCM[1] = make_float2(m.cm0.z, m.cm0.w);
+    t.pCM[2] = make_float2(m.cm1.x, m.cm1.y); t.pCM[3] = make_float2(m.cm1.z, m.cm1.w);
+    t.dcA = make_float2(m.cDC.x, m.cDC.y); t.dcB = make_float2(m.cDC.z, m.cDC.w);
+    t.ix = m.ix;
     dM = Mach - t.bM; dA = alpha - t.bA; dH = h - t.bH;
-    CYa = bilinear(t.cCY, dM, dA) * cy_gain;
+    cm = bilinear2(t.pCM, dM, make_float2(dA, dA));
+    cm.x *= cy_gain;
   }
   int iC = t.ix >> 24;
-  const float4 qC = axis_seek<ft::AXC, ft::NC>(sT, CYa, iC);
+  const float4 qC = axis_seek<ft::AXC, ft::NC>(sT, cm.x, iC);
   t.bC = qC.x; t.wC = qC.y;
-  t.cCX = sT[ft::T_MC + iC * ft::NM + (t.ix & 31)];
-  dC = CYa - t.bC;
+  const float4 cx = sT[ft::T_MC + iC * ft::NM + (t.ix & 31)];
+  t.cxA = make_float2(cx.x, cx.y); t.cxB = make_float2(cx.z, cx.w);
+  dC = cm.x - t.bC;
   t.ix = (t.ix & 0x00ffffffu) | (uint32_t)iC << 24;
 }
 
@@ -340,16 +352,18 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   TabCache& tc = r.tc;
   const float cy_gain = GEN ? r.sumA[1] : 1.0f;
   float dM = Mach - tc.bM, dA = alpha - tc.bA, dH = h - tc.bH;
-  float CYa = bilinear(tc.cCY, dM, dA);
-  if (GEN) CYa *= cy_gain;
-  float dC = CYa - tc.bC;
+  float2 cm = bilinear2(tc.pCM, dM, make_float2(dA, dA));  // (CYa, mz)
+  if (GEN) cm.x *= cy_gain;
+  float dC = cm.x - tc.bC;
   const bool missMAH = axis_miss(dM, tc.wM) | axis_miss(dA, tc.wA) | axis_miss(dH, tc.wH);
-  if (missMAH | axis_miss(dC, tc.wC)) tab_update(sT, Mach, alpha, h, cy_gain, missMAH, tc, dM, dA, dH, CYa, dC);
-  float mz = bilinear(tc.cMZ, dM, dA);
-  float CXa = bilinear(tc.cCX, dM, dC);
+  if (__builtin_expect(missMAH | axis_miss(dC, tc.wC), 0))
+    tab_update(sT, Mach, alpha, h, cy_gain, missMAH, tc, dM, dA, dH, cm, dC);
+  const float2 dMM = make_float2(dM, dM);
+  const float2 ix = __ffma2_rn(tc.cxA, dMM, tc.cxB), id = __ffma2_rn(tc.dcA, dMM, tc.dcB);  // inner terms (c3 dM + c2, c1 dM + c0)
+  const float CYa = cm.x;
+  float mz = cm.y, CXa = fmaf(ix.x, dC, ix.y), dCm = fmaf(id.x, dH, id.y);
   if (GEN) CXa *= r.sumA[0];
   o.CYa = CYa; o.CXa = CXa;
-  float dCm = bilinear(tc.cDC, dH, dM);
   float Ka = fmaf(tc.k1, dA, tc.k0);
   if (GEN) { dCm *= r.sumA[3]; Ka *= r.sumA[4]; mz *= r.sumA[2]; }
   o.dCm = dCm; o.K_alpha = Ka; o.mz = mz;
@@ -448,10 +462,14 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
               y_wz = __double2float_rn(r.wz), y_ssi = __double2float_rn(r.ssi), y_ssf = __double2float_rn(r.ssf),
               y_th = __double2float_rn(r.th);
   const float vref_f = __double2float_rn(r.vartheta);
-  float X_h = y_h, X_Vx = y_Vx, X_Vy = y_Vy, X_wz = y_wz, X_ssi = y_ssi, X_ssf = y_ssf, d_th = 0.f;
+  // RK4 bookkeeping in register PAIRS (packed FFMA2, the weights ride as broadcast scalars): the stage state pair
+  // (Vy, wz) is at the same time the derivative of (h, theta); (Vx, ssi) and (ssf, int dvartheta) pair up likewise.
+  const float2 yVW = make_float2(y_Vy, y_wz), yXI = make_float2(y_Vx, y_ssi);
+  float2 XVW = yVW, XXI = yXI;  // (X_Vy, X_wz), (X_Vx, X_ssi)
+  float X_h = y_h, X_ssf = y_ssf, d_th = 0.f;
   double X_th = r.th, Xd_h = r.h, X_csi = r.csi, X_csf = r.csf;
-  float a_h = 0, a_Vx = 0, a_Vy = 0, a_wz = 0, a_ssi = 0, a_ssf = 0, a_th = 0, a_x = 0;
-  float a_dvi = 0, a_itse = 0;
+  float2 aHT = make_float2(0.f, 0.f), aVW = aHT, aXI = aHT, aFD = aHT;  // sums for (h, th) (Vy, wz) (Vx, ssi) (ssf, dvi)
+  float a_x = 0, a_itse = 0;
   double a_csi = 0, a_csf = 0;
   bool memout_ss = false, memout_cs = false;
   float u_n = 0.f;
@@ -467,7 +485,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
     const float t_f = s == 0 ? t0f : (s == 3 ? t0f + hh : t0f + hhalf);
     float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_itse;
     double f_csi, f_csf;
-    pass32<TIER>(sT, mp, c, s, n, X_th, d_th, tg, vref_f, t_f, X_h, Xd_h, X_Vx, X_Vy, X_wz, X_ssi, X_ssf, X_csi, X_csf, r, at,
+    pass32<TIER>(sT, mp, c, s, n, X_th, d_th, tg, vref_f, t_f, X_h, Xd_h, XXI.x, XVW.x, XVW.y, XXI.y, X_ssf, X_csi, X_csf, r, at,
                 memout_ss, memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
     if (s == 0) {
       // update(): discrete filter, rate-limiter memory, Memory blocks, Derivative history, delay push
@@ -479,33 +497,43 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
       r.d2_u = __double2float_rn(dvdt_major);
       u_n = o.U_com;
     }
-    const float w = ends ? 1.f : 2.f;
+    const float2 fVW = make_float2(f_Vy, f_wz), fXI = make_float2(f_Vx, f_ssi), fFD = make_float2(f_ssf, o.dvf);
     const double wd = ends ? 1.0 : 2.0;
-    a_h = fmaf(w, f_h, a_h); a_Vx = fmaf(w, f_Vx, a_Vx); a_Vy = fmaf(w, f_Vy, a_Vy); a_wz = fmaf(w, f_wz, a_wz);
-    a_ssi = fmaf(w, f_ssi, a_ssi); a_ssf = fmaf(w, f_ssf, a_ssf); a_th = fmaf(w, X_wz, a_th);
+    if (s == 0) {  // first term of the sums: plain copies
+      aHT = XVW; aVW = fVW; aXI = fXI; aFD = fFD; a_itse = f_itse;
+      if (want_x) a_x = XXI.x;
+    } else {
+      const float w = ends ? 1.f : 2.f;
+      const float2 ww = make_float2(w, w);
+      aHT = __ffma2_rn(ww, XVW, aHT); aVW = __ffma2_rn(ww, fVW, aVW); aXI = __ffma2_rn(ww, fXI, aXI);
+      aFD = __ffma2_rn(ww, fFD, aFD);
+      a_itse = fmaf(w, f_itse, a_itse);
+      if (want_x) a_x = fmaf(w, XXI.x, a_x);
+    }
     if (CS) { a_csi = fma(wd, f_csi, a_csi); a_csf = fma(wd, f_csf, a_csf); }
-    if (want_x) a_x = fmaf(w, X_Vx, a_x);
-    a_dvi = fmaf(w, o.dvf, a_dvi);
-    a_itse = fmaf(w, f_itse, a_itse);
     if (s < 3) {
       const float cf = (s == 2) ? hh : hhalf;
       const double cfd = (s == 2) ? kH : 0.5 * kH;
       if (s == 2) {  // integral / position signals at stage 4 = y + h*f2
         s4.dvi = r.dvi + (double)(hh * o.dvf);
         s4.itse = r.itse + (double)(hh * f_itse);
-        s4.x = want_x ? (float)r.x + hh * X_Vx : 0.f;
-        X_th = fma(kH, (double)X_wz, r.th);  // theta' = wz: the full-step pass needs the float64 pitch
+        s4.x = want_x ? (float)r.x + hh * XXI.x : 0.f;
+        X_th = fma(kH, (double)XVW.y, r.th);  // theta' = wz: the full-step pass needs the float64 pitch
       } else {
-        d_th = cf * X_wz;                    // half-step passes: float32 pitch increment since the major pass
+        d_th = cf * XVW.y;                   // half-step passes: float32 pitch increment since the major pass
       }
-      X_h = fmaf(cf, f_h, y_h); X_Vx = fmaf(cf, f_Vx, y_Vx); X_Vy = fmaf(cf, f_Vy, y_Vy); X_wz = fmaf(cf, f_wz, y_wz);
-      X_ssi = fmaf(cf, f_ssi, y_ssi); X_ssf = fmaf(cf, f_ssf, y_ssf);
+      const float2 cc = make_float2(cf, cf);
+      X_h = fmaf(cf, f_h, y_h);
+      XVW = __ffma2_rn(cc, fVW, yVW); XXI = __ffma2_rn(cc, fXI, yXI);
+      X_ssf = fmaf(cf, f_ssf, y_ssf);
       if (CS) {
         X_csi = fma(cfd, f_csi, r.csi); X_csf = fma(cfd, f_csf, r.csf);
         Xd_h = fma(cfd, (double)f_h, r.h);
       }
     }
   }
+  const float X_Vx = XXI.x, X_Vy = XVW.x, X_wz = XVW.y;
+  const float a_h = aHT.x, a_th = aHT.y, a_Vy = aVW.x, a_wz = aVW.y, a_Vx = aXI.x, a_ssi = aXI.y, a_ssf = aFD.x, a_dvi = aFD.y;
   s4.h = X_h; s4.Vx = X_Vx; s4.Vy = X_Vy; s4.wz = X_wz;
   const float h6 = (float)(kH / 6.0);
   const double h6d = kH / 6.0;

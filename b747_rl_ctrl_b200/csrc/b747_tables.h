@@ -25,8 +25,10 @@
 // Layout (float4 units, staged into shared memory by every block of k_env_step32):
 //   axis record, one per interval i:      {bp[i], bp[i+1]-bp[i], k0, k1}; (k0, k1) = K_alpha(alpha) = k0 + k1 d
 //                                         on the alpha axis, 0 elsewhere.  The alpha axis is in radians.
-//   2-D cell (i0 along axis 0, i1 axis 1): {c0, c1, c2, c3}
-//   CYa and mz share both axes; their cells are interleaved (2 float4 per cell).
+//   2-D cell (d0 = Mach offset for every table, d1 = the other operand's offset): CXa and dCm cells are stored as
+//   {c3, c1, c2, c0}: one packed FFMA2 (c3, c1) dM + (c2, c0) gives both inner terms, one FFMA finishes the table
+//   CYa and mz share both axes; their cells are interleaved component-wise, {cy0, mz0, cy1, mz1} {cy2, mz2, cy3, mz3},
+//   so that two 128-bit loads fill four aligned register pairs for packed FFMA2 evaluation of both tables at once.
 //   coarse index map per axis: LUT_N bytes, bucket b of the flight-envelope range -> interval holding the bucket's lower
 //                                         edge; the first search of a launch starts there (the kernel then walks 0..2 steps)
 // Host-only code (no CUDA types); the device side reads it through the offsets below.
@@ -44,7 +46,7 @@ namespace ft {
 
 constexpr int NM = 17, NA = 23, NH = 6, NC = 15;  // intervals per merged + extended axis (checked by build())
 constexpr int AXM = 0, AXA = AXM + NM, AXH = AXA + NA, AXC = AXH + NH;  // float4 offsets
-constexpr int T_HM = AXC + NC;           // dCm cells  [iM][iH]      d0 = h offset,    d1 = Mach offset
+constexpr int T_HM = AXC + NC;           // dCm cells  [iM][iH]      d0 = Mach offset, d1 = h offset
 constexpr int T_MC = T_HM + NM * NH;     // CXa cells  [iC][iM]      d0 = Mach offset, d1 = CYa offset
 constexpr int T_MA = T_MC + NC * NM;     // CYa,mz cells [iA][iM][2] d0 = Mach offset, d1 = alpha offset (rad)
 constexpr int LUT = T_MA + 2 * NA * NM;   // 4 coarse index maps (Mach, alpha, h, CYa), LUT_N bytes each
@@ -143,21 +145,28 @@ inline Fast build() {
     q[3] = (float)(((t11 - t01) - (t10 - t00)) / (w0 * w1));
   };
   auto wd = [](const std::vector<double>& b, int i, double unit) { return (b[i + 1] - b[i]) / unit; };
+  auto cell_inner = [&](float* q, double t00, double t10, double t01, double t11, double w0, double w1) {
+    float c[4];
+    cell(c, t00, t10, t01, t11, w0, w1);
+    q[0] = c[3]; q[1] = c[1]; q[2] = c[2]; q[3] = c[0];
+  };
   for (int iM = 0; iM < NM; iM++)
     for (int iH = 0; iH < NH; iH++)
-      cell(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], O.dCm(F.bH[iH], F.bM[iM]), O.dCm(F.bH[iH + 1], F.bM[iM]),
-           O.dCm(F.bH[iH], F.bM[iM + 1]), O.dCm(F.bH[iH + 1], F.bM[iM + 1]), wd(F.bH, iH, 1.0), wd(F.bM, iM, 1.0));
+      cell_inner(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], O.dCm(F.bH[iH], F.bM[iM]), O.dCm(F.bH[iH], F.bM[iM + 1]),
+           O.dCm(F.bH[iH + 1], F.bM[iM]), O.dCm(F.bH[iH + 1], F.bM[iM + 1]), wd(F.bM, iM, 1.0), wd(F.bH, iH, 1.0));
   for (int iC = 0; iC < NC; iC++)
     for (int iM = 0; iM < NM; iM++)
-      cell(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], O.CXa(F.bM[iM], F.bC[iC]), O.CXa(F.bM[iM + 1], F.bC[iC]),
+      cell_inner(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], O.CXa(F.bM[iM], F.bC[iC]), O.CXa(F.bM[iM + 1], F.bC[iC]),
            O.CXa(F.bM[iM], F.bC[iC + 1]), O.CXa(F.bM[iM + 1], F.bC[iC + 1]), wd(F.bM, iM, 1.0), wd(F.bC, iC, 1.0));
   for (int iA = 0; iA < NA; iA++)
     for (int iM = 0; iM < NM; iM++) {
       float* q = &F.v[(size_t)(T_MA + 2 * (iA * NM + iM)) * 4];
-      cell(q, O.CYa(F.bM[iM], F.bA[iA]), O.CYa(F.bM[iM + 1], F.bA[iA]), O.CYa(F.bM[iM], F.bA[iA + 1]),
+      float cy[4], mz[4];
+      cell(cy, O.CYa(F.bM[iM], F.bA[iA]), O.CYa(F.bM[iM + 1], F.bA[iA]), O.CYa(F.bM[iM], F.bA[iA + 1]),
            O.CYa(F.bM[iM + 1], F.bA[iA + 1]), wd(F.bM, iM, 1.0), wd(F.bA, iA, rad));
-      cell(q + 4, O.mz(F.bM[iM], F.bA[iA]), O.mz(F.bM[iM + 1], F.bA[iA]), O.mz(F.bM[iM], F.bA[iA + 1]),
+      cell(mz, O.mz(F.bM[iM], F.bA[iA]), O.mz(F.bM[iM + 1], F.bA[iA]), O.mz(F.bM[iM], F.bA[iA + 1]),
            O.mz(F.bM[iM + 1], F.bA[iA + 1]), wd(F.bM, iM, 1.0), wd(F.bA, iA, rad));
+      for (int k = 0; k < 4; k++) { q[2 * k] = cy[k]; q[2 * k + 1] = mz[k]; }
     }
   auto lut = [&](int k, const std::vector<double>& b, double lo, double hi) {
     unsigned char* L = reinterpret_cast<unsigned char*>(&F.v[(size_t)LUT * 4]) + k * LUT_N;
@@ -187,6 +196,9 @@ inline int find(const Fast& F, int off, int n, double u) {
 inline double bil(const float* c, double d0, double d1) {
   return ((double)c[0] + (double)c[1] * d0) + ((double)c[2] + (double)c[3] * d0) * d1;
 }
+inline double bil_inner(const float* q, double d0, double d1) {  // {c3, c1, c2, c0} cells
+  return ((double)q[3] + (double)q[1] * d0) + ((double)q[2] + (double)q[0] * d0) * d1;
+}
 struct FastEval {
   const Fast& F;
   void eval(double M, double a, double h, double out[5]) const {  // a in degrees; CYa, CXa, dCm, mz, Ka
@@ -196,11 +208,12 @@ struct FastEval {
     auto off = [&](int ax, int i, double u) { return u - (double)F.v[(size_t)(ax + i) * 4]; };
     const double dM = off(AXM, iM, M), dA = off(AXA, iA, ar), dH = off(AXH, iH, h);
     const float* q = &F.v[(size_t)(T_MA + 2 * (iA * NM + iM)) * 4];
-    out[0] = bil(q, dM, dA);
-    out[3] = bil(q + 4, dM, dA);
+    const float cy[4] = {q[0], q[2], q[4], q[6]}, mz[4] = {q[1], q[3], q[5], q[7]};
+    out[0] = bil(cy, dM, dA);
+    out[3] = bil(mz, dM, dA);
     const int iC = find(F, AXC, NC, out[0]);
-    out[1] = bil(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], dM, off(AXC, iC, out[0]));
-    out[2] = bil(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], dH, dM);
+    out[1] = bil_inner(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], dM, off(AXC, iC, out[0]));
+    out[2] = bil_inner(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], dM, dH);
     const float* k = &F.v[(size_t)(AXA + iA) * 4];
     out[4] = (double)k[2] + dA * (double)k[3];
   }

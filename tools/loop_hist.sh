@@ -9,12 +9,18 @@ ins=[]
 for l in L:
     m=re.match(r'\s+/\*([0-9a-f]{4})\*/\s+(.*?);',l)
     ins.append((int(m.group(1),16),m.group(2).strip()))
-best=None
+loops=[]
 for a,t in ins:
     m=re.search(r'BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)',t)
     if m:
         tgt=int(m.group(1),16)
-        if tgt<a and (best is None or a-tgt>best[1]-best[0]): best=(tgt,a)
+        if tgt<a: loops.append((tgt,a))
+loops.sort(key=lambda l:l[0]-l[1])
+# the K loop is the largest loop nested inside the persistent tile loop (or the largest one if there is no tile loop)
+best=loops[0]
+for l in loops[1:]:
+    if l[0]>=loops[0][0] and l[1]<=loops[0][1] and (l[1]-l[0])*3>(loops[0][1]-loops[0][0]):
+        best=l; break
 print("loop 0x%x..0x%x  %d instructions"%(best[0],best[1],(best[1]-best[0])//16+1))
 c=collections.Counter()
 for a,t in ins:
