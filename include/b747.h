@@ -77,7 +77,7 @@ typedef struct b747_cfg {
 /* Per-episode initial condition and reference (what Controller.reset decides, core/controller.py:134-201). */
 typedef struct b747_episode {
   double state0[6];        /* x, y, Vx, Vy, vartheta, wz  (core/model.py:226) */
-  int32_t use_ctrl;        /* altitude loop (СУ PID) closed (Controller.use_ctrl, core/controller.py:150-163) */
+  int32_t use_ctrl;        /* altitude loop (СУ PID) closed; only honoured with B747_RESET_HYBRID (else ctrl_type decides) */
   int32_t oscillating;
   double vref_const;
   double osc_A[3], osc_f[3];
