@@ -148,6 +148,28 @@ def cpu_reference_rate(steps, warmup, env_steps_per_worker, substeps=SUBSTEPS):
     return value, {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, total / steps
 
 
+def python_loop_rate(n_steps=20000, substeps=SUBSTEPS):
+    """a gym-style Python loop, one `env.step(a)` call per env step on the DLL-backed env layer, one
+    core.  An upper bound for any Python-side ControllerEnv (the reference's wrappers add ~50 ctypes property accesses
+    per step; its published end-to-end figure is 240-360 env-steps/s)."""
+    import numpy as np
+    from oracle import dllref
+    from oracle import oracle as O
+    if not dllref.available():
+        return None
+    env = O.RefEnv(O.make_cfg(sample_time=substeps * 0.01, seed=1), env_id=0)
+    env.reset()
+    acts = np.random.default_rng(0).uniform(-1, 1, n_steps)
+    t = time.perf_counter()
+    for a in acts:
+        _, _, d = env.step(a)
+        if d:
+            env.reset()
+    dt = time.perf_counter() - t
+    return {"value": n_steps / dt, "unit": UNIT, "cores": 1,
+            "sample": f"{n_steps} env.step(a) calls from a Python loop, K={substeps}, reference DLL + C env layer"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -305,6 +327,7 @@ def run_cuda(args, rank, local_rank, world):
     if world == 1 and not args.no_cpu_baseline:
         try:
             _, info, _ = cpu_reference_rate(3, 1, 300000)
+            info["python_step_loop"] = python_loop_rate()
             line["cpu_baseline"] = info
         except Exception as e:  # the CPU leg must never hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "error", "sample": repr(e)}
@@ -318,11 +341,13 @@ def _emit(line):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process (native libraries write to fd 1 directly)
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process (native libraries write to fd 1 directly)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
