@@ -184,6 +184,27 @@ def run_reference(args, rank, world):
     _emit(line)
 
 
+def _bind_near_gpu(torch, local_rank):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs NVML reports as local to its GPU: with 8 ranks
+    the host legs of the e2e path otherwise cross sockets.  Best effort; returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(ncpu, 1024) + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {i for i in allowed if (words[i // 64] >> (i % 64)) & 1}
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} of {len(allowed)} cpus (GPU-local)"
+        return f"{len(allowed)} cpus (no narrower GPU-local set)"
+    except Exception as e:  # NVML missing / restricted: keep the default affinity
+        return f"default ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------------------
 def run_cuda(args, rank, local_rank, world):
     import numpy as np
@@ -194,6 +215,7 @@ def run_cuda(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = _bind_near_gpu(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_local = N_ENVS_PER_GPU
@@ -320,7 +342,7 @@ def run_cuda(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
                     "d2h_bytes_per_step": (12 + 4 + 1) * n_local, "steps": e2e_steps,
                     "api": "b747_step_host (C ABI, pinned host buffers; 8-chunk copy/step/copy pipeline replayed as a CUDA graph)",
-                    "gpu_launches": int(e2e_launches)},
+                    "gpu_launches": int(e2e_launches), "host_affinity": affinity},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "episode_stats": summarize(stats)}
