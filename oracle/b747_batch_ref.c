@@ -2,9 +2,13 @@
  * b747_batch_ref.c -- TEST INFRASTRUCTURE (oracle), not product code.
  * N independent (restatement model + env layer) pairs stepped in a loop: the CPU
  * checker the GPU parity tests compare against, and bench.py's "port" cpu_baseline.
+ * Environments are independent, so large batches are stepped by a few pthreads (the 4096-env x 1000-step
+ * parity case of BASELINE configs[1] then takes seconds on the host cores).
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "b747_oracle.h"
 
@@ -42,15 +46,46 @@ void b747o_batch_reset_to(b747o_batch *b, const b747o_episode *eps, double *obs)
   for (int64_t i = 0; i < b->n; i++) b747o_env_reset_to(&b->envs[i], &eps[i], obs + i * b->envs[i].obs_dim);
 }
 
+typedef struct {
+  b747o_batch *b;
+  const double *actions;
+  double *obs, *rew, *terminal_obs;
+  uint8_t *done;
+  int auto_reset;
+  int64_t lo, hi;
+} step_job;
+
+static void *step_range(void *arg) {
+  step_job *j = arg;
+  for (int64_t i = j->lo; i < j->hi; i++) {
+    b747o_env *e = &j->b->envs[i];
+    int od = e->obs_dim;
+    int d = b747o_env_step(e, j->actions[i], j->obs + i * od, j->rew + i);
+    j->done[i] = (uint8_t)d;
+    if (j->terminal_obs) memcpy(j->terminal_obs + i * od, j->obs + i * od, sizeof(double) * od);
+    if (d && j->auto_reset) b747o_env_reset(e, j->obs + i * od);
+  }
+  return NULL;
+}
+
 void b747o_batch_step(b747o_batch *b, const double *actions, double *obs, double *rew, uint8_t *done,
                       double *terminal_obs, int auto_reset) {
-  for (int64_t i = 0; i < b->n; i++) {
-    b747o_env *e = &b->envs[i];
-    int od = e->obs_dim;
-    int d = b747o_env_step(e, actions[i], obs + i * od, rew + i);
-    done[i] = (uint8_t)d;
-    if (terminal_obs) memcpy(terminal_obs + i * od, obs + i * od, sizeof(double) * od);
-    if (d && auto_reset) b747o_env_reset(e, obs + i * od);
+  enum { MAXT = 32 };
+  long nt = b->n >= 256 ? sysconf(_SC_NPROCESSORS_ONLN) : 1;
+  if (nt > MAXT) nt = MAXT;
+  if (nt < 1) nt = 1;
+  step_job jobs[MAXT];
+  pthread_t th[MAXT];
+  int started[MAXT] = {0};
+  for (long t = 0; t < nt; t++) {
+    step_job j = {b, actions, obs, rew, terminal_obs, done, auto_reset, b->n * t / nt, b->n * (t + 1) / nt};
+    jobs[t] = j;
+    if (t > 0 && pthread_create(&th[t], NULL, step_range, &jobs[t]) == 0) started[t] = 1;
+  }
+  step_range(&jobs[0]);
+  for (long t = 1; t < nt; t++) {
+    if (started[t]) pthread_join(th[t], NULL);
+    else step_range(&jobs[t]);  /* thread creation failed: run the slice here */
   }
 }
 

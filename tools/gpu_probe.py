@@ -66,7 +66,7 @@ def variants():
     from tests.test_gpu_parity import VARIANTS
     for name, kw in sorted(VARIANTS.items()):
         steps = 320 if name == "K1_tk3" else 420
-        n = 96
+        n = 512
         cfg_o = O.make_cfg(seed=9, **kw)
         eng = E.BatchEngine(n_envs=n, dtype=E.F32, seed=9, auto_reset=True, **kw)
         ob = O.OracleBatch(cfg_o, n)
