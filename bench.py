@@ -341,7 +341,7 @@ def run_cuda(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
                     "d2h_bytes_per_step": (12 + 4 + 1) * n_local, "steps": e2e_steps,
-                    "api": "b747_step_host (C ABI, pinned host buffers; 8-chunk copy/step/copy pipeline replayed as a CUDA graph)",
+                    "api": "b747_step_host (C ABI, pinned host buffers; 4-chunk copy/step/copy pipeline replayed as a CUDA graph)",
                     "gpu_launches": int(e2e_launches), "host_affinity": affinity},
             "gpu_launches": int(launches),
             "roofline": roofline,

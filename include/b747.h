@@ -118,7 +118,7 @@ int b747_step(b747_handle *h, const void *actions_dev, void *obs_dev, void *rew_
  * pipelined over env chunks (copy-in, step and copy-out of neighbouring chunks overlap; pinned buffers
  * are needed for the overlap, pageable ones still work); results are identical to the one-launch form. */
 int b747_step_host(b747_handle *h, const void *actions, void *obs, void *rew, uint8_t *done, void *terminal_obs);
-/* Number of chunks of b747_step_host's pipeline: 0 = automatic (8 from 128 Ki envs, else 1), 1 = no pipeline. */
+/* Number of chunks of b747_step_host's pipeline: 0 = automatic (4 from 128 Ki envs, else 1), 1 = no pipeline. */
 int b747_set_host_chunks(b747_handle *h, int n_chunks);
 
 /* Raw model stepping (Model.step xN, core/model.py:247-250): no action law, no reward (f64 handles).
