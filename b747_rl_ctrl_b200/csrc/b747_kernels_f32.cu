@@ -26,6 +26,16 @@ enum { DG_h_th = 0, DG_V, DG_wz_ssi, DG_ssf_dvi, DG_itse_d1, DG_vref_ret, DG_cs,
 enum { FG_act = 0, FG_uh, FG_misc, FG_sumA, FG_misc2, NF_GROUPS };
 static_assert(DG_vref_ret == 5 && FG_misc == 2, "stage_issue copies D groups 0-5 and F groups 0-2");
 
+// The tick word of F[FG_misc] also carries the look-up interval indices between launches (no extra HBM bytes): bit 31
+// set = {tick in bits 0-13, indices in bits 14-30}; bit 31 clear = plain tick (episodes beyond 16383 ticks), no indices.
+__device__ __forceinline__ void unpack_tick(uint32_t w, int& tick, uint32_t& ix) {
+  if (w & 0x80000000u) { tick = (int)(w & 0x3fffu); ix = (w >> 14) & 0x1ffffu; }
+  else { tick = (int)w; ix = kIxEmpty; }
+}
+__device__ __forceinline__ uint32_t pack_tick(int tick, uint32_t ix) {
+  return ((unsigned)tick < 0x4000u && ix != kIxEmpty) ? (0x80000000u | (ix & 0x1ffffu) << 14 | (uint32_t)tick) : (uint32_t)tick;
+}
+
 template <bool GEN>
 __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, RegsMx& r) {
   const double2* __restrict__ D = st.D;
@@ -40,7 +50,9 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
   float4 f;
   f = F[FG_act * np + i]; r.df_x = f.x; r.df_y = f.y; r.rl_prev = f.z; r.deltaz = f.w;
   f = F[FG_uh * np + i]; r.uh[0] = f.x; r.uh[1] = f.y; r.uh[2] = f.z; r.uh[3] = f.w;
-  f = F[FG_misc * np + i]; r.sig_upid = f.x; r.d2_u = f.y; r.tick = __float_as_int(f.z);
+  f = F[FG_misc * np + i]; r.sig_upid = f.x; r.d2_u = f.y;
+  uint32_t ix_hint;
+  unpack_tick(__float_as_uint(f.z), r.tick, ix_hint);
   const unsigned fw = __float_as_uint(f.w);
   r.flags = (int)(fw & 0xffu); r.ep_idx = fw >> 8;
   if (GEN) {
@@ -60,8 +72,8 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
     r.tf_tp = 0.f; r.sig_vzh = 0.f;
   }
   r.vartheta = 0.0;
-  r.tc = TabCache{};  // look-up cache: zero widths = nothing cached, refilled on first use
-  r.tc.ix = 0xffffffffu;
+  r.tc = TabCache{};  // look-up cache: zero widths = nothing cached, refilled on first use (from the persisted indices)
+  r.tc.ix = ix_hint;
 }
 
 // ---- TMA staging of the canonical (LEAN) state: each warp owns a 4.5 KB shared-memory buffer; one elected lane issues
@@ -114,7 +126,9 @@ __device__ __forceinline__ void load_mx_staged(const unsigned char* buf, int lan
   float4 f;
   f = F[FG_act * 32 + lane]; r.df_x = f.x; r.df_y = f.y; r.rl_prev = f.z; r.deltaz = f.w;
   f = F[FG_uh * 32 + lane]; r.uh[0] = f.x; r.uh[1] = f.y; r.uh[2] = f.z; r.uh[3] = f.w;
-  f = F[FG_misc * 32 + lane]; r.sig_upid = f.x; r.d2_u = f.y; r.tick = __float_as_int(f.z);
+  f = F[FG_misc * 32 + lane]; r.sig_upid = f.x; r.d2_u = f.y;
+  uint32_t ix_hint;
+  unpack_tick(__float_as_uint(f.z), r.tick, ix_hint);
   const unsigned fw = __float_as_uint(f.w);
   r.flags = (int)(fw & 0xffu); r.ep_idx = fw >> 8;
   r.csi = r.csf = r.x = 0.0; r.href = B747_DEF_H_ZH;
@@ -125,7 +139,7 @@ __device__ __forceinline__ void load_mx_staged(const unsigned char* buf, int lan
   r.tf_tp = 0.f; r.sig_vzh = 0.f;
   r.vartheta = 0.0;
   r.tc = TabCache{};
-  r.tc.ix = 0xffffffffu;
+  r.tc.ix = ix_hint;
 }
 
 // `full`: also the groups a step never changes (reference, aero sums, state0) -- reset paths only.
@@ -141,7 +155,7 @@ __device__ __forceinline__ void store_mx(const StateF32& st, size_t np, int i, c
   D[DG_vref_ret * np + i] = make_double2(r.vref, r.ep_return);
   F[FG_act * np + i] = make_float4(r.df_x, r.df_y, r.rl_prev, r.deltaz);
   F[FG_uh * np + i] = make_float4(r.uh[0], r.uh[1], r.uh[2], r.uh[3]);
-  F[FG_misc * np + i] = make_float4(r.sig_upid, r.d2_u, __int_as_float(r.tick),
+  F[FG_misc * np + i] = make_float4(r.sig_upid, r.d2_u, __uint_as_float(pack_tick(r.tick, r.tc.ix)),
                                     __uint_as_float(((unsigned)r.flags & 0xffu) | (r.ep_idx << 8)));
   if (GEN) {
     D[DG_cs * np + i] = make_double2(r.csi, r.csf);
@@ -485,6 +499,7 @@ __global__ void __launch_bounds__(128) k_defaults32(DevCfg c, StateF32 st) {
   const double s0[6] = B747_DEF_STATE0;
   r.flags = (c.ctrl_type == B747_CTRL_SEMI_MANUAL || c.ctrl_type == B747_CTRL_FULL_AUTO) ? FL_USE_CTRL : 0;
   r.ep_idx = 0;
+  r.tc.ix = kIxEmpty;
   for (int k = 0; k < 5; k++) r.sumA[k] = 1.0f;
   model_init32(s0, r);
   r.vref = 0.0; r.href = B747_DEF_H_ZH; r.vartheta = 0.0;
@@ -635,9 +650,10 @@ int f32_field_io(const DevCfg& c, StateF32& s, int kind, int row, const char* na
     for (size_t i = 0; i < n; i++) {
       uint32_t tz, fw;
       memcpy(&tz, &tmp[i].z, 4); memcpy(&fw, &tmp[i].w, 4);
-      if (out) out[i] = kind == 3 ? (double)(int)tz : (kind == 4 ? (double)(fw & 0xffu) : (double)(fw >> 8));
+      const int tick = (tz & 0x80000000u) ? (int)(tz & 0x3fffu) : (int)tz;  // unpack_tick
+      if (out) out[i] = kind == 3 ? (double)tick : (kind == 4 ? (double)(fw & 0xffu) : (double)(fw >> 8));
       else {
-        if (kind == 3) tz = (uint32_t)(int)in[i];
+        if (kind == 3) tz = (uint32_t)(int)in[i] & 0x7fffffffu;  // plain tick: the interval hints are dropped
         else if (kind == 4) fw = (fw & ~0xffu) | ((uint32_t)in[i] & 0xffu);
         else fw = (fw & 0xffu) | ((uint32_t)in[i] << 8);
         memcpy(&tmp[i].z, &tz, 4); memcpy(&tmp[i].w, &fw, 4);

@@ -68,7 +68,8 @@ struct TabCache {
   // cells as coefficient PAIRS for packed FFMA2 evaluation, y = (c0 + c1 dM) + (c2 + c3 dM) d1 with d1 = dA / dC / dH:
   float2 pCM[4];                         // (CYa, mz) coefficient pairs k = 0..3 (the two tables share both operands)
   float2 cxA, cxB, dcA, dcB;             // CXa and dCm cells as (c3, c1) and (c2, c0): inner terms by one FFMA2
-  uint32_t ix;                           // interval indices iM | iA << 8 | iH << 16 | iC << 24 (read by the refill only)
+  uint32_t ix;                           // interval indices iM | iA << 5 | iH << 10 | iC << 13, kIxEmpty = none (read by the
+                                         // refill only; persisted between launches in the spare bits of the tick word)
 };
 
 // float copies of the uniform tunables + folded constants (built on the host, b747_kernels_f32.cu)
@@ -177,12 +178,15 @@ __device__ __forceinline__ float2 bilinear2(const float2 p[4], float d0, float2 
 //    the fully inlined form doubled the loop to 26 KB and tripled the no_instruction stalls).
 //  * CYa miss -- the common case, CYa crosses its 0.1-wide intervals with every degree of alpha: a few inline
 //    instructions move the interval and reload the CXa cell.
+constexpr uint32_t kIxEmpty = 0xffffffffu;
 struct TabMAH { float bM, wM, bA, wA, bH, wH, k0, k1; float4 cm0, cm1, cDC; uint32_t ix; };
 
 __device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float Mach, float alpha, float h, float cy_gain,
                                             uint32_t ix, TabMAH* __restrict__ out) {
-  int iM = ix & 31, iA = (ix >> 8) & 31, iH = (ix >> 16) & 7, iC = ix >> 24;
-  const bool empty = ix == 0xffffffffu;
+  int iM = ix & 31, iA = (ix >> 5) & 31, iH = (ix >> 10) & 7, iC = (ix >> 13) & 15;
+  const bool empty = ix == kIxEmpty;
+  // indices restored from HBM are only hints (the state may have been edited): keep them on their axes
+  iM = min(iM, ft::NM - 1); iA = min(iA, ft::NA - 1); iH = min(iH, ft::NH - 1); iC = min(iC, ft::NC - 1);
   constexpr float rad = (float)Pc(21);
   if (empty) {
     iM = axis_guess<0>(sT, Mach, (float)ft::LUT_M_LO, (float)(ft::LUT_N / (ft::LUT_M_HI - ft::LUT_M_LO)));
@@ -201,7 +205,7 @@ __device__ __noinline__ void tab_refill_mah(const float4* __restrict__ sT, float
     const float CYa = bilinear(make_float4(t.cm0.x, t.cm0.z, t.cm1.x, t.cm1.z), Mach - t.bM, alpha - t.bA) * cy_gain;
     iC = axis_guess<3>(sT, CYa, (float)ft::LUT_C_LO, (float)(ft::LUT_N / (ft::LUT_C_HI - ft::LUT_C_LO)));
   }
-  t.ix = (uint32_t)iM | (uint32_t)iA << 8 | (uint32_t)iH << 16 | (uint32_t)iC << 24;
+  t.ix = (uint32_t)iM | (uint32_t)iA << 5 | (uint32_t)iH << 10 | (uint32_t)iC << 13;
   *out = t;
 }
 
@@ -219,13 +223,13 @@ __device__ __forceinline__ void tab_update(const float4* __restrict__ sT, float 
     cm = bilinear2(t.pCM, dM, make_float2(dA, dA));
     cm.x *= cy_gain;
   }
-  int iC = t.ix >> 24;
+  int iC = (t.ix >> 13) & 15;
   const float4 qC = axis_seek<ft::AXC, ft::NC>(sT, cm.x, iC);
   t.bC = qC.x; t.wC = qC.y;
   const float4 cx = sT[ft::T_MC + iC * ft::NM + (t.ix & 31)];
   t.cxA = make_float2(cx.x, cx.y); t.cxB = make_float2(cx.z, cx.w);
   dC = cm.x - t.bC;
-  t.ix = (t.ix & 0x00ffffffu) | (uint32_t)iC << 24;
+  t.ix = (t.ix & 0x1fffu) | (uint32_t)iC << 13;
 }
 
 // Atmosphere of one model step: evaluated in full at the major pass, carried to the three minor passes by its first
