@@ -174,6 +174,31 @@ def test_f32_variants_within_bound(E, oracle, name):
     assert q[1] <= 1.0
 
 
+@pytest.mark.parametrize("dtype_name", ["F64", "F32"])
+def test_config0_single_env_10k_steps(E, dtype_name):
+    """BASELINE configs[0]: ONE environment, 10 000 env steps (50 000 model steps) of fixed-seed random elevator actions,
+    against the digest of the trajectory the reference DLL produced (tests/golden/make_config0.py): episodic (25
+    resets) and one 100 s flight (tk = 1e9; the f32 handle then runs with tick > 16383, the plain tick word)."""
+    import sys
+    sys.path.insert(0, HERE)
+    from config0_check import check_config0
+    g = json.load(open(os.path.join(HERE, "golden", "config0_golden.json")))
+    dtype = getattr(E, dtype_name)
+    a = np.random.default_rng(g["action_seed"]).uniform(-1.0, 1.0, g["n_steps"])
+    for name, kw in (("episodic", {}), ("long_flight", dict(tk=1.0e9))):
+        eng = E.BatchEngine(n_envs=1, dtype=dtype, seed=g["seed"], auto_reset=True, **kw)
+        eng.reset()
+        n = g["n_steps"]
+        obs = np.zeros((n, 3)); rew = np.zeros(n); done = np.zeros(n, dtype=bool)
+        term = np.zeros((1, 3), eng.np_dtype)
+        for k in range(n):
+            _, r, d, term = eng.step_host(a[k:k + 1], terminal_obs=term)
+            obs[k], rew[k], done[k] = term[0], r[0], d[0]
+        tol = (2e-9, 1e-9) if dtype == E.F64 else (1e-5, 2e-3)
+        check_config0(g["cases"][name], obs, rew, done, *tol)
+        eng.close()
+
+
 def test_full_size_properties_config3(E, oracle):
     """BASELINE configs[2]: 1M envs, f32, K=10, in-kernel auto-reset -- size-independent properties."""
     import torch
