@@ -6,12 +6,16 @@
 //   D[g][env] : double2   g = 0:(h,th) 1:(Vx,Vy) 2:(wz,ssi) 3:(ssf,dvi) 4:(itse,d1_u) 5:(vref,ep_return)
 //                             6:(csi,csf) 7:(x,href) 8..10: oscillating-reference (A0,A1)(A2,f0)(f1,f2)
 //                             11..13: state0
-//   F[g][env] : float4    g = 0:(df_x,df_y,rl_prev,deltaz) 1:(uh0..uh3) 2:(sig_upid,d2_u,tick,flags|episode<<8)
+//   F[g][env] : float4    g = 0:(df_x,df_y,rl_prev,deltaz) 1:(uh0..uh3) 2:(sig_upid,d2_u,tick|look-up hints,flags|episode<<8)
 //                             3:(sumA0..3) 4:(sumA4,tf_tp,sig_vzh,-)
 // so each thread moves its state with 128-bit loads/stores and a warp touches one contiguous 512-byte
 // segment per group.  The canonical configuration (LEAN) reads and writes groups D0-5 and F0-2 only:
 // 144 B in + 144 B out per env step, plus action (4) obs (12) reward (4) done (1) = 309 B/env-step,
 // independent of K.
+//
+// Three instantiations of the step kernel (launch_env_step32 picks one per handle): tier 0 the canonical family on the
+// LEAN layout, tier 1 the general layout without the altitude loop, tier 2 everything (altitude loop, recorder / tracker,
+// signal export).  All are persistent-warp kernels: grid = SMs x resident blocks, tables staged once per block.
 #include <string.h>
 
 #include <vector>
