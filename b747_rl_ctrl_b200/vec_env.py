@@ -6,9 +6,12 @@ observation, infos[i]["terminal_observation"] holds the last one and infos[i]["e
 {"r", "l", "t"} record VecMonitor would add.
 
 Two I/O modes:
-  * numpy (default; what SB3 passes): one H2D copy of the actions and one D2H copy of obs/rew/done
-    per step through b747_step_host;
+  * numpy (default; what SB3 passes): actions are staged in a pinned host buffer and obs/rew/done land in pinned
+    buffers, so b747_step_host runs its chunked copy/step/copy pipeline as one CUDA-graph launch per step;
   * torch device tensors (`device_tensors=True`): obs/rew/done stay in HBM, for GPU-resident policies.
+
+When stable-baselines3 is importable the class derives from its `VecEnv`, so `PPO('MlpPolicy', env)` takes it as is
+(`BaseAlgorithm._wrap_env` wraps anything that is not a `VecEnv` instance into a DummyVecEnv).
 """
 import time
 
@@ -19,13 +22,35 @@ from .env.ctrl_env import ObservationType, RewardType, make_spaces
 from .core.controller import CtrlMode, CtrlType
 
 
+try:  # a real SB3 VecEnv where SB3 exists (not in this image: no network), a duck type otherwise
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:
+    _VecEnvBase = object
+
+
+def _pinned(shape, dtype):
+    """Page-locked numpy array (a view of a pinned torch tensor, kept alive by the returned pair); pageable if torch
+    cannot pin here."""
+    try:
+        import torch
+        t = torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+        return t.numpy(), t
+    except Exception:
+        return np.zeros(shape, dtype), None
+
+
+def th_index(t, idx):
+    import torch
+    return torch.as_tensor(idx, device=t.device, dtype=torch.long)
+
+
 def _val(x, default=None):
     if x is None:
         return default
     return x.value if hasattr(x, "value") else int(x)
 
 
-class B747VecEnv:
+class B747VecEnv(_VecEnvBase):
     def __init__(self, num_envs, observation_type=ObservationType.PID_LIKE, reward_type=RewardType.CLASSIC,
                  norm_obs=True, norm_act=True, ctrl_type=CtrlType.MANUAL, ctrl_mode=CtrlMode.DIRECT_CONTROL,
                  reset_ref_mode=None, disturbance_mode=None, tk=20, sample_time=0.05, action_max=17 * np.pi / 180,
@@ -44,20 +69,28 @@ class B747VecEnv:
             env_id_offset=env_id_offset)
         self.num_envs = int(num_envs)
         self.observation_space, self.action_space = make_spaces(observation_type, norm_obs, norm_act, action_max)
+        if _VecEnvBase is not object:
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
         self.device_tensors = bool(device_tensors)
         self.monitor = bool(monitor)
         self.tk, self.sample_time, self.action_max, self.vartheta_max = tk, sample_time, action_max, vartheta_max
         self._t0 = time.time()
         self._actions = None
+        # SB3 wants one info dict per env and step; building 10^5..10^6 dicts per step would dominate the step, so the
+        # empty ones are shared between steps and only the environments that finished get a fresh dict
+        self._no_infos = [{} for _ in range(self.num_envs)]
         od = self.engine.obs_dim
         if self.device_tensors:
             self._act_d, self._obs_d, self._rew_d, self._done_d, self._term_d = self.engine.alloc_io(terminal_obs=True)
         else:
             dt = self.engine.np_dtype
-            self._obs = np.zeros((self.num_envs, od), dt)
-            self._rew = np.zeros(self.num_envs, dt)
-            self._done = np.zeros(self.num_envs, np.uint8)
-            self._term = np.zeros((self.num_envs, od), dt)
+            self._keep = []
+            for name, shape, d in (("_act_h", (self.num_envs,), dt), ("_obs", (self.num_envs, od), dt),
+                                   ("_rew", (self.num_envs,), dt), ("_done", (self.num_envs,), np.uint8),
+                                   ("_term", (self.num_envs, od), dt)):
+                arr, owner = _pinned(shape, d)
+                setattr(self, name, arr)
+                self._keep.append(owner)
 
     # ---- VecEnv API ------------------------------------------------------------------------
     def reset(self):
@@ -83,12 +116,12 @@ class B747VecEnv:
             self.engine.step(self._act_d, self._obs_d, self._rew_d, self._done_d, self._term_d)
             self.engine.synchronize()
             done_any = bool(self._done_d.any().item())
-            infos = self._infos(self._done_d.cpu().numpy(), self._term_d) if done_any else [{}] * self.num_envs
+            infos = self._infos(self._done_d.cpu().numpy(), self._term_d) if done_any else self._no_infos
             return self._obs_d, self._rew_d, self._done_d.bool(), infos
-        a = np.asarray(a).reshape(self.num_envs)
-        self.engine.step_host(a, self._obs, self._rew, self._done, self._term)
+        np.copyto(self._act_h, np.asarray(a).reshape(self.num_envs), casting="unsafe")
+        self.engine.step_host(self._act_h, self._obs, self._rew, self._done, self._term)
         done = self._done.astype(bool)
-        infos = self._infos(self._done, self._term) if done.any() else [{} for _ in range(self.num_envs)]
+        infos = self._infos(self._done, self._term) if done.any() else self._no_infos
         return self._obs.copy(), self._rew.copy(), done, infos
 
     def step(self, actions):
@@ -96,16 +129,18 @@ class B747VecEnv:
         return self.step_wait()
 
     def _infos(self, done, term):
-        infos = [{} for _ in range(self.num_envs)]
+        infos = list(self._no_infos)
         idx = np.nonzero(done)[0]
         if len(idx):
             ret, ln = self.engine.last_episode() if self.monitor else (None, None)
             t = round(time.time() - self._t0, 6)
-            for i in idx:
-                ti = term[i]
-                infos[i]["terminal_observation"] = ti.clone() if hasattr(ti, "clone") else np.array(ti)
+            dev = hasattr(term, "cpu")
+            rows = term[idx] if not dev else term[th_index(term, idx)]
+            for j, i in enumerate(idx):
+                info = {"terminal_observation": rows[j].clone() if dev else rows[j].copy()}
                 if self.monitor:
-                    infos[i]["episode"] = {"r": float(ret[i]), "l": int(ln[i]), "t": t}
+                    info["episode"] = {"r": float(ret[i]), "l": int(ln[i]), "t": t}
+                infos[i] = info
         return infos
 
     def close(self):
