@@ -49,12 +49,23 @@ class ActorCritic(nn.Module):
         return self.vf(obs).squeeze(-1)
 
 
+def _log_prob(a, mean, log_std):
+    # Normal(mean, exp(log_std)).log_prob(a), written out (no distribution objects inside captured graphs)
+    return -0.5 * ((a - mean) * torch.exp(-log_std)) ** 2 - log_std - 0.5 * math.log(2 * math.pi)
+
+
 def train(n_envs=65536, total_steps=None, threshold=225.0, max_seconds=600.0, n_steps=32, n_minibatches=16, n_epochs=4,
           lr=3e-4, gamma=0.99, gae_lambda=0.95, clip=0.2, vf_coef=0.5, ent_coef=0.0, max_grad_norm=0.5, seed=1, device=0,
-          env_kwargs=None, log=None, desync=True):
+          env_kwargs=None, log=None, desync=True, use_graphs=True, tf32=True):
+    """PPO with SB3's defaults.  use_graphs: the T-step rollout (policy, sampling, env kernel, GAE) and one epoch of
+    minibatch updates are each captured ONCE as a CUDA graph and replayed -- the eager form spends 98 % of a rollout step
+    in launch overhead of ~30 tiny policy kernels around a 0.02 ms environment step."""
     torch.manual_seed(seed)
     dev = torch.device("cuda", device)
     torch.cuda.set_device(dev)
+    if tf32:  # the 64-wide MLP GEMMs on the tensor cores (fp32 accumulate); SB3's own default on Ampere+ GPUs as well
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     kw = dict(sample_time=0.05, tk=20.0)  # main.py:18, 95-96: K = 5, 400-step episodes
     kw.update(env_kwargs or {})
     eng = E.BatchEngine(n_envs=n_envs, dtype=E.F32, device=device, seed=seed, auto_reset=True, **kw)
@@ -75,28 +86,27 @@ def train(n_envs=65536, total_steps=None, threshold=225.0, max_seconds=600.0, n_
         eng.step(act, obs, rew, done)
         eng.episode_stats()  # discard the warm-up episodes
     net = ActorCritic(od).to(dev)
-    opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-5)
+    opt = torch.optim.Adam(net.parameters(), lr=lr, eps=1e-5, capturable=use_graphs)
     T, N = n_steps, n_envs
     b_obs = torch.empty(T, N, od, device=dev); b_act = torch.empty(T, N, device=dev); b_logp = torch.empty(T, N, device=dev)
     b_val = torch.empty(T, N, device=dev); b_rew = torch.empty(T, N, device=dev); b_done = torch.empty(T, N, device=dev)
+    adv = torch.empty(T, N, device=dev); ret = torch.empty(T, N, device=dev)
     mb = T * N // n_minibatches
-    steps_done, updates = 0, 0
-    history = []
-    t_hit = None
-    ep_n = ep_sum = 0.0
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    while True:
+    perm = torch.empty(T * N, dtype=torch.long, device=dev)
+    f_obs, f_act, f_logp = b_obs.view(-1, od), b_act.view(-1), b_logp.view(-1)
+    f_adv, f_ret = adv.view(-1), ret.view(-1)
+    params = list(net.parameters())
+
+    def rollout():
         with torch.no_grad():
             for t in range(T):
-                d = net.dist(obs)
-                a = d.sample()
-                b_obs[t] = obs; b_act[t] = a; b_logp[t] = d.log_prob(a); b_val[t] = net.value(obs)
+                mean = net.pi(obs).squeeze(-1)
+                a = mean + torch.exp(net.log_std) * torch.randn_like(mean)
+                b_obs[t] = obs; b_act[t] = a; b_logp[t] = _log_prob(a, mean, net.log_std); b_val[t] = net.value(obs)
                 torch.clamp(a, -1.0, 1.0, out=act)   # SB3 clips the action to the Box before env.step
                 eng.step(act, obs, rew, done)        # one kernel launch; obs is the reset observation where done
                 b_rew[t] = rew; b_done[t] = done
             last_val = net.value(obs)
-            adv = torch.empty_like(b_rew)
             gae = torch.zeros(N, device=dev)
             for t in reversed(range(T)):
                 nonterm = 1.0 - b_done[t]
@@ -104,25 +114,77 @@ def train(n_envs=65536, total_steps=None, threshold=225.0, max_seconds=600.0, n_
                 delta = b_rew[t] + gamma * nxt * nonterm - b_val[t]
                 gae = delta + gamma * gae_lambda * nonterm * gae
                 adv[t] = gae
-            ret = adv + b_val
-        f_obs, f_act, f_logp = b_obs.view(-1, od), b_act.view(-1), b_logp.view(-1)
-        f_adv, f_ret = adv.view(-1), ret.view(-1)
+            torch.add(adv, b_val, out=ret)
+
+    def minibatch(k):
+        idx = perm[k * mb:(k + 1) * mb]
+        o_mb = f_obs[idx]
+        logp = _log_prob(f_act[idx], net.pi(o_mb).squeeze(-1), net.log_std)
+        a_mb = f_adv[idx]
+        a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
+        ratio = (logp - f_logp[idx]).exp()
+        pg = -torch.min(ratio * a_mb, ratio.clamp(1 - clip, 1 + clip) * a_mb).mean()
+        v_loss = ((net.value(o_mb) - f_ret[idx]) ** 2).mean()
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + net.log_std).mean()
+        loss = pg + vf_coef * v_loss - ent_coef * entropy
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        # clip_grad_norm_ without a host read
+        tot = torch.sqrt(sum((p.grad.detach() ** 2).sum() for p in params))
+        scale = torch.clamp(max_grad_norm / (tot + 1e-6), max=1.0)
+        for p in params:
+            p.grad.mul_(scale)
+        opt.step()
+
+    def epoch():
+        for k in range(n_minibatches):
+            minibatch(k)
+
+    g_roll = g_epoch = None
+    if use_graphs:
+        try:
+            # warm-up on a side stream (allocator, autograd and optimizer state), then capture each phase once
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eng.use_stream(side.cuda_stream)
+                perm.copy_(torch.randperm(T * N, device=dev))
+                rollout()
+                minibatch(0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_roll, g_epoch = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # the env kernel is launched through the C ABI on the handle's stream: point it at the capture stream first
+            # (b747_set_stream synchronises, which is not allowed once the capture has begun)
+            with torch.cuda.graph(g_roll, stream=side):
+                rollout()
+            with torch.cuda.graph(g_epoch, stream=side):
+                epoch()
+            eng.use_stream(torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            eng.episode_stats()  # the warm-up / capture steps do not count
+        except Exception as e:  # capture not available: eager
+            if log:
+                log(f"CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
+            g_roll = g_epoch = None
+            eng.use_stream(torch.cuda.current_stream().cuda_stream)
+    steps_done, updates = 0, 0
+    history = []
+    t_hit = None
+    ep_n = ep_sum = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    while True:
+        if g_roll is not None:
+            g_roll.replay()
+        else:
+            rollout()
         for _ in range(n_epochs):
-            perm = torch.randperm(T * N, device=dev)
-            for k in range(n_minibatches):
-                idx = perm[k * mb:(k + 1) * mb]
-                d = net.dist(f_obs[idx])
-                logp = d.log_prob(f_act[idx])
-                a_mb = f_adv[idx]
-                a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
-                ratio = (logp - f_logp[idx]).exp()
-                pg = -torch.min(ratio * a_mb, ratio.clamp(1 - clip, 1 + clip) * a_mb).mean()
-                v_loss = ((net.value(f_obs[idx]) - f_ret[idx]) ** 2).mean()
-                loss = pg + vf_coef * v_loss - ent_coef * d.entropy().mean()
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                nn.utils.clip_grad_norm_(net.parameters(), max_grad_norm)
-                opt.step()
+            perm.copy_(torch.randperm(T * N, device=dev))
+            if g_epoch is not None:
+                g_epoch.replay()
+            else:
+                epoch()
         steps_done += T * N
         updates += 1
         st = eng.episode_stats()  # in-kernel episode statistics since the last call (the only host read per update)
@@ -143,7 +205,7 @@ def train(n_envs=65536, total_steps=None, threshold=225.0, max_seconds=600.0, n_
     eng.close()
     return dict(steps=steps_done, seconds=wall, steps_per_s=steps_done / wall, updates=updates, history=history,
                 threshold=threshold, reached=(None if t_hit is None else dict(seconds=t_hit[0], steps=t_hit[1], ep_rew_mean=t_hit[2])),
-                final_ep_rew_mean=(history[-1][2] if history else None), net=net)
+                final_ep_rew_mean=(history[-1][2] if history else None), net=net, graphs=g_roll is not None)
 
 
 def main():
@@ -156,9 +218,10 @@ def main():
     ap.add_argument("--epochs", type=int, default=4)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA-graph capture of the rollout / update phases")
     a = ap.parse_args()
     r = train(n_envs=a.envs, threshold=a.threshold, max_seconds=a.max_seconds, n_steps=a.n_steps, n_minibatches=a.minibatches,
-              n_epochs=a.epochs, lr=a.lr, log=None if a.quiet else print)
+              n_epochs=a.epochs, lr=a.lr, log=None if a.quiet else print, use_graphs=not a.eager)
     r.pop("net"); hist = r.pop("history")
     r["history_tail"] = hist[-5:]
     r["config"] = dict(envs=a.envs, n_steps=a.n_steps, minibatches=a.minibatches, epochs=a.epochs, lr=a.lr,
