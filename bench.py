@@ -297,26 +297,29 @@ def run_cuda(args, rank, local_rank, world):
     kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
     # ---- the same kernel at K = 1 (Controller's default sample_time = dt): the HBM-bound end of the K axis
     # (only near K = 1 can the step approach the HBM roof; reported beside the K = 10 headline)
-    k1 = None
+    k1 = k5 = None
     if world == 1:
-        e1 = E.BatchEngine(n_envs=n_local, dtype=E.F32, device=local_rank, sample_time=0.01, seed=1, auto_reset=True)
-        e1.use_stream(stream.cuda_stream)
-        e1.reset(obs)
-        for i in range(5):
-            e1.step(pool[i % 8], obs, rew, done)
-        n1 = max(20, min(args.steps, 200))
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        torch.cuda.synchronize()
-        ev1[0].record()
-        for i in range(n1):
-            e1.step(pool[i % 8], obs, rew, done)
-        ev1[1].record()
-        torch.cuda.synchronize()
-        ms1 = ev1[0].elapsed_time(ev1[1]) / n1
-        ach1 = BYTES_PER_ENV_STEP * n_local / (ms1 * 1e-3) / 1e9
-        k1 = {"substeps": 1, "kernel_ms": ms1, "env_steps_per_s": n_local / (ms1 * 1e-3), "achieved": ach1, "peak": peak,
-              "unit": "GB/s", "frac": ach1 / peak, "steps": n1}
-        e1.close()
+        def other_k(K):
+            e1 = E.BatchEngine(n_envs=n_local, dtype=E.F32, device=local_rank, sample_time=K * 0.01, seed=1, auto_reset=True)
+            e1.use_stream(stream.cuda_stream)
+            e1.reset(obs)
+            for i in range(5):
+                e1.step(pool[i % 8], obs, rew, done)
+            n1 = max(20, min(args.steps, 200))
+            ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            torch.cuda.synchronize()
+            ev1[0].record()
+            for i in range(n1):
+                e1.step(pool[i % 8], obs, rew, done)
+            ev1[1].record()
+            torch.cuda.synchronize()
+            ms1 = ev1[0].elapsed_time(ev1[1]) / n1
+            ach1 = BYTES_PER_ENV_STEP * n_local / (ms1 * 1e-3) / 1e9
+            e1.close()
+            return {"substeps": K, "kernel_ms": ms1, "env_steps_per_s": n_local / (ms1 * 1e-3), "achieved": ach1,
+                    "peak": peak, "unit": "GB/s", "frac": ach1 / peak, "steps": n1}
+        k1 = other_k(1)   # Controller's default sample_time = dt
+        k5 = other_k(5)   # the reference's own training value (main.py: sample_time = 0.05)
     achieved = BYTES_PER_ENV_STEP * n_local / (kernel_ms * 1e-3) / 1e9
     prof = {}
     pj = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -331,7 +334,7 @@ def run_cuda(args, rank, local_rank, world):
                 "kernel": "b747::k_env_step32<false>", "kernel_ms": kernel_ms,
                 "note": ("K=10 substeps make the kernel FP32/XU-pipe bound, not HBM bound (SURVEY.md 8d); "
                          "pipe utilisation from ncu is in profiles/"),
-                "pipes": prof.get("pipes"), "k1": k1}
+                "pipes": prof.get("pipes"), "k1": k1, "k5": k5}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
