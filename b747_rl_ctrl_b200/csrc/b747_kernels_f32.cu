@@ -40,7 +40,9 @@ __device__ __forceinline__ uint32_t pack_tick(int tick, uint32_t ix) {
   return ((unsigned)tick < 0x4000u && ix != kIxEmpty) ? (0x80000000u | (ix & 0x1ffffu) << 14 | (uint32_t)tick) : (uint32_t)tick;
 }
 
-template <bool GEN>
+// CSF = false (step kernel, tier 1): the altitude-loop states and h_zh are neither read nor integrated, so they are not
+// carried through the step at all (8 registers); a reset inside the step writes their fresh values (store_mx, full).
+template <bool GEN, bool CSF = true>
 __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, RegsMx& r) {
   const double2* __restrict__ D = st.D;
   const float4* __restrict__ F = st.F;
@@ -60,8 +62,13 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
   const unsigned fw = __float_as_uint(f.w);
   r.flags = (int)(fw & 0xffu); r.ep_idx = fw >> 8;
   if (GEN) {
-    d = D[DG_cs * np + i]; r.csi = d.x; r.csf = d.y;
-    d = D[DG_x_href * np + i]; r.x = d.x; r.href = d.y;
+    if (CSF) {
+      d = D[DG_cs * np + i]; r.csi = d.x; r.csf = d.y;
+      d = D[DG_x_href * np + i]; r.x = d.x; r.href = d.y;
+    } else {
+      r.csi = r.csf = 0.0; r.href = 0.0;
+      r.x = ((const double*)(D + DG_x_href * np + i))[0];
+    }
     d = D[DG_osc0 * np + i]; r.oscA[0] = d.x; r.oscA[1] = d.y;
     d = D[DG_osc1 * np + i]; r.oscA[2] = d.x; r.oscf[0] = d.y;
     d = D[DG_osc2 * np + i]; r.oscf[1] = d.x; r.oscf[2] = d.y;
@@ -147,7 +154,7 @@ __device__ __forceinline__ void load_mx_staged(const unsigned char* buf, int lan
 }
 
 // `full`: also the groups a step never changes (reference, aero sums, state0) -- reset paths only.
-template <bool GEN>
+template <bool GEN, bool CSF = true>
 __device__ __forceinline__ void store_mx(const StateF32& st, size_t np, int i, const RegsMx& r, bool full) {
   double2* __restrict__ D = st.D;
   float4* __restrict__ F = st.F;
@@ -162,8 +169,12 @@ __device__ __forceinline__ void store_mx(const StateF32& st, size_t np, int i, c
   F[FG_misc * np + i] = make_float4(r.sig_upid, r.d2_u, __uint_as_float(pack_tick(r.tick, r.tc.ix)),
                                     __uint_as_float(((unsigned)r.flags & 0xffu) | (r.ep_idx << 8)));
   if (GEN) {
-    D[DG_cs * np + i] = make_double2(r.csi, r.csf);
-    D[DG_x_href * np + i] = make_double2(r.x, r.href);
+    if (CSF || full) {
+      D[DG_cs * np + i] = make_double2(r.csi, r.csf);
+      D[DG_x_href * np + i] = make_double2(r.x, r.href);
+    } else {
+      ((double*)(D + DG_x_href * np + i))[0] = r.x;
+    }
     F[FG_misc2 * np + i] = make_float4(r.sumA[4], r.tf_tp, r.sig_vzh, 0.f);
     if (full) {
       D[DG_osc0 * np + i] = make_double2(r.oscA[0], r.oscA[1]);
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
   }
   if (live) {
     if (!STAGED) {
-      load_mx<GEN>(st, np, i, r);
+      load_mx<GEN, CS>(st, np, i, r);
       a = actions[i];
     }
     if (c.norm_act) a *= (float)c.action_max;
@@ -319,12 +330,12 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
     }
     PassMx o;
     Stage4Mx s4;
-    const bool tracing = GEN && (st.trace.trk || st.trace.rec);
+    const bool tracing = CS && (st.trace.trk || st.trace.rec);  // recorder / tracker / signal export: tier 2 only
     const bool want_x = GEN && (c.obs_type == B747_OBS_MODEL_STATE || tracing);
 #pragma unroll 1
     for (int k = 0; k < c.substeps; k++) {
       model_step32<TIER>(sT, mp, c, r, o, s4, want_x);
-      if (GEN && tracing) {  // Controller._post_step (core/controller.py:209-228)
+      if (CS && tracing) {  // Controller._post_step (core/controller.py:209-228)
         TraceSample ts;
         ts.t = (double)r.tick * kH; ts.U_com = o.U_com; ts.U_PID = o.U_com_PID; ts.deltaz_RP = o.deltaz_RP;
         ts.hzh = r.href; ts.vref = use_ctrl ? (double)o.vartheta_zh : r.vartheta; ts.U_RL = a;
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
           for (int k = 0; k < n; k++) obs[k] /= mx[k];
       }
     }
-    if (GEN && st.trace.trk) {  // Controller.quality of the running episode
+    if (CS && st.trace.trk) {  // Controller.quality of the running episode
       const double q = exp(-60 * 0.1 * s4.itse / (c.tk * ((double)vr * (double)vr)));
       st.trace.trk[(size_t)TRK_quality * np + i] = q;
       st.trace.trk[((size_t)NTRK + TRK_quality) * np + i] = q;
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
     done = (int64_t)r.tick >= c.done_tick;
     if (c.use_limiter && (fabsf(nan_to_num_f(o.th)) > (float)(5 * kPi / 180 + c.vartheta_max) || r.deltaz > (float)c.action_max))
       done = true;
-    if (GEN && st.sig) {  // signal export: general kernel only (f32_is_lean)
+    if (CS && st.sig) {  // signal export: full tier only (launch_env_step32)
       float* sg = st.sig;
 #define SG(name, v) sg[(size_t)SIG_##name * np + i] = (v)
       const float qn = nanf("");
@@ -439,16 +450,16 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
     if (done) {
       ep_ret = r.ep_return; ep_len = (double)(r.tick / c.substeps);
       st.last_ret[i] = ep_ret; st.last_len[i] = r.tick / c.substeps;
-      if (GEN && st.trace.trk) trace_snapshot(st.trace, np, i, st.trace.trk[(size_t)TRK_quality * np + i]);
+      if (CS && st.trace.trk) trace_snapshot(st.trace, np, i, st.trace.trk[(size_t)TRK_quality * np + i]);
       if (c.auto_reset) {
-        if (GEN) trace_clear(st.trace, np, i);
+        if (CS) trace_clear(st.trace, np, i);
         Episode ep;
         if (c.reset_ref_mode == B747_RESET_NONE) episode_from_state_mx(st, np, i, r, ep);
         else { draw_episode(c, (uint64_t)(c.env_id_offset + i), r.ep_idx, ep); r.ep_idx++; }
         env_reset_mx<GEN>(c, ep, r, st, np, i);
         full_store = true;
         for (int k = 0; k < od; k++) obs[k] = 0.f;
-        if (GEN && st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
+        if (CS && st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
       }
     }
     if (od == 3) {  // canonical layout: three contiguous floats per env
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
     } else {
       for (int k = 0; k < od; k++) obs_out[(size_t)i * od + k] = obs[k];
     }
-    store_mx<GEN>(st, np, i, r, full_store);
+    store_mx<GEN, CS>(st, np, i, r, full_store);
   }
   warp_episode_stats(s_stats, done, ep_ret, ep_len);
   }
