@@ -252,7 +252,7 @@ __device__ __forceinline__ void load_tables32(float4* sT, const float4* __restri
 #endif
 // TIER 0: canonical family (LEAN layout); 1: general layout without the altitude loop (other observation layouts,
 // oscillating references, aero disturbance, TF reward, signal export, trace); 2: + the altitude loop (СУ PID).
-template <int TIER>
+template <int TIER, int SW = -1>
 __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER == 1 ? B747_EXT_MINBLOCKS : B747_F32_MINBLOCKS)) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                     uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
         r.vartheta = r.vref;
       }
     }
-    if (!(mp.sw & SW_SS_ON)) {
+    if (!((SW >= 0 ? SW : mp.sw) & SW_SS_ON)) {
       const float lim = (float)(17 * kPi / 180);
       float dz;
       switch (c.ctrl_mode) {
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
     const bool want_x = GEN && (c.obs_type == B747_OBS_MODEL_STATE || tracing);
 #pragma unroll 1
     for (int k = 0; k < c.substeps; k++) {
-      model_step32<TIER>(sT, mp, c, r, o, s4, want_x);
+      model_step32<TIER, SW>(sT, mp, c, r, o, s4, want_x);
       if (CS && tracing) {  // Controller._post_step (core/controller.py:209-228)
         TraceSample ts;
         ts.t = (double)r.tick * kH; ts.U_com = o.U_com; ts.U_PID = o.U_com_PID; ts.deltaz_RP = o.deltaz_RP;
@@ -606,7 +606,9 @@ void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions
   const int n = c.env_hi - c.env_lo;
   if (n <= 0) return;
   const bool plain = !st.trace.trk && !st.trace.rec && !st.sig && !c.force_full;
-  if (plain && f32_is_lean(c))
+  if (plain && f32_is_lean(c) && mp.sw == SW_RP)  // the canonical switch setting (use_RP only) as a compile-time constant
+    k_env_step32<0, SW_RP><<<step_grid<0>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+  else if (plain && f32_is_lean(c))
     k_env_step32<0><<<step_grid<0>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && !f32_needs_cs(c))
     k_env_step32<1><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);

@@ -249,7 +249,8 @@ struct TrigMx { float sn, cs, thf, sgn, ub, wb, rV, alpha; double thd; };
 // Passes 0 and 3 -- the ones whose pitch error is differenced by the Derivative blocks, observed and rewarded -- carry
 // the pitch angle and the pitch error in float64 (th_d); the half-step passes only feed float32 RK4 sums and use th_f.
 // TIER 0: canonical (LEAN) model; 1: + aero-disturbance gains (general layout, no altitude loop); 2: + the altitude loop (СУ PID)
-template <int TIER>
+// SW >= 0: the diagram's manual switches as a compile-time constant (the canonical env: SW_RP only); -1: read mp.sw
+template <int TIER, int SW = -1>
 __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, int stage, int n,
                                        double th_d, float dth, TrigMx& tg, float vref_f, float t_f, float h, double h_d, float Vx,
                                        float Vy, float wz, float ssi, float ssf, double csi, double csf, RegsMx& r,
@@ -422,11 +423,12 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   const float ss_d = (dv * mp.PID_SS[2] - ssf) * mp.PID_SS[3];
   const float ss_pre = fmaf(dv, mp.PID_SS[0], ssi) + ss_d;
   o.U_com_PID = satf(ss_pre, PCF(5), PCF(7));
-  if (mp.sw & SW_RL) o.U_com = PCF(147) > fabsf(o.U_com_PID) ? 0.f : o.U_com_PID;
-  else o.U_com = (mp.sw & SW_SS) ? o.U_com_PID : r.deltaz;
+  const int sw = SW >= 0 ? SW : mp.sw;
+  if (sw & SW_RL) o.U_com = PCF(147) > fabsf(o.U_com_PID) ? 0.f : o.U_com_PID;
+  else o.U_com = (sw & SW_SS) ? o.U_com_PID : r.deltaz;
   const float ax = fmaf(Fx, cs, -sn * Fy);
   const float ay = fmaf(Fy, cs, fmaf(Fx, sn, -mp.g));
-  const float dze = (mp.sw & SW_RP) ? o.deltaz_RP : o.U_com;
+  const float dze = (sw & SW_RP) ? o.deltaz_RP : o.U_com;
   const float Cm = fmaf(PCF(217) * dCm * Ka, dze * PCF(150), mz);
   const float wzd = Cm * (rV2 * mp.half_Sc_over_Iz);
   // clamping anti-windup (СС)
@@ -454,7 +456,7 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
 
 // model_simple_step in the mixed formulation.  On return r holds the post-update state, `o` the
 // stage-4 pass and s4 the stage-4 (predictor) state values.
-template <int TIER>
+template <int TIER, int SW = -1>
 __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, const MP32& mp, const DevCfg& c, RegsMx& r,
                                              PassMx& o, Stage4Mx& s4, bool want_x) {
   constexpr bool CS = TIER >= 2;
@@ -489,7 +491,7 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
     const float t_f = s == 0 ? t0f : (s == 3 ? t0f + hh : t0f + hhalf);
     float f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_itse;
     double f_csi, f_csf;
-    pass32<TIER>(sT, mp, c, s, n, X_th, d_th, tg, vref_f, t_f, X_h, Xd_h, XXI.x, XVW.x, XVW.y, XXI.y, X_ssf, X_csi, X_csf, r, at,
+    pass32<TIER, SW>(sT, mp, c, s, n, X_th, d_th, tg, vref_f, t_f, X_h, Xd_h, XXI.x, XVW.x, XVW.y, XXI.y, X_ssf, X_csi, X_csf, r, at,
                 memout_ss, memout_cs, o, f_h, f_Vx, f_Vy, f_wz, f_ssi, f_ssf, f_csi, f_csf, f_itse);
     if (s == 0) {
       // update(): discrete filter, rate-limiter memory, Memory blocks, Derivative history, delay push
