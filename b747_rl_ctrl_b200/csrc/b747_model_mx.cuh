@@ -366,18 +366,21 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   const float2 dMM = make_float2(dM, dM);
   const float2 ix = __ffma2_rn(tc.cxA, dMM, tc.cxB), id = __ffma2_rn(tc.dcA, dMM, tc.dcB);  // inner terms (c3 dM + c2, c1 dM + c0)
   const float CYa = cm.x;
-  float mz = cm.y, CXa = fmaf(ix.x, dC, ix.y), dCm = fmaf(id.x, dH, id.y);
-  if (GEN) CXa *= r.sumA[0];
-  o.CYa = CYa; o.CXa = CXa;
+  // cx = P126 CXa and dcm = P217 P150 dCm: the cells carry the diagram's gains (b747_tables.h)
+  float mz = cm.y, cx = fmaf(ix.x, dC, ix.y), dcm = fmaf(id.x, dH, id.y);
+  if (GEN) cx *= r.sumA[0];
   float Ka = fmaf(tc.k1, dA, tc.k0);
-  if (GEN) { dCm *= r.sumA[3]; Ka *= r.sumA[4]; mz *= r.sumA[2]; }
-  o.dCm = dCm; o.K_alpha = Ka; o.mz = mz;
+  if (GEN) { dcm *= r.sumA[3]; Ka *= r.sumA[4]; mz *= r.sumA[2]; }
+  o.CYa = CYa; o.K_alpha = Ka; o.mz = mz;
+  if (GEN) {  // the signals themselves are only read by observation layouts / exports of the general tiers
+    o.CXa = cx * (float)(1.0 / Pc(126));
+    o.dCm = dcm * (float)(1.0 / (Pc(217) * Pc(150)));
+  }
   // aerodynamic + thrust acceleration in body axes, straight from the body velocity components:
   // drag/lift rotated by alpha with sin(alpha) = -wb/V, cos(alpha) = ub/V gives
   //   Fx = q S (c_x ub - CYa wb)/V + P,  Fy = q S (CYa ub + c_x wb)/V,  q S / V = rho V S / 2,  c_x = P126 CXa
   const float rV2 = rho * V2;
   const float kq = rV2 * (rV * mp.kS_m);
-  const float cx = PCF(126) * CXa;
   const float Fx = fmaf(kq, fmaf(-CYa, wb, cx * ub), mp.P_m);
   const float Fy = kq * fmaf(cx, wb, CYa * ub);
   // actuator: transport delay (3 steps) -> discrete filter (every 5th tick) -> rate limiter -> saturation
@@ -429,7 +432,7 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   const float ax = fmaf(Fx, cs, -sn * Fy);
   const float ay = fmaf(Fy, cs, fmaf(Fx, sn, -mp.g));
   const float dze = (sw & SW_RP) ? o.deltaz_RP : o.U_com;
-  const float Cm = fmaf(PCF(217) * dCm * Ka, dze * PCF(150), mz);
+  const float Cm = fmaf(dcm * Ka, dze, mz);
   const float wzd = Cm * (rV2 * mp.half_Sc_over_Iz);
   // clamping anti-windup (СС)
   const float dz = ss_pre - o.U_com_PID;

@@ -27,6 +27,8 @@
 //                                         on the alpha axis, 0 elsewhere.  The alpha axis is in radians.
 //   2-D cell (d0 = Mach offset for every table, d1 = the other operand's offset): CXa and dCm cells are stored as
 //   {c3, c1, c2, c0}: one packed FFMA2 (c3, c1) dM + (c2, c0) gives both inner terms, one FFMA finishes the table
+//   The CXa cells carry the gain P126 of the drag path and the dCm cells the gains P217 P150 of the elevator-moment path
+//   (constants of the diagram between the look-up and its only consumer), so the kernel multiplies neither.
 //   CYa and mz share both axes; their cells are interleaved component-wise, {cy0, mz0, cy1, mz1} {cy2, mz2, cy3, mz3},
 //   so that two 128-bit loads fill four aligned register pairs for packed FFMA2 evaluation of both tables at once.
 //   coarse index map per axis: LUT_N bytes, bucket b of the flight-envelope range -> interval holding the bucket's lower
@@ -94,6 +96,10 @@ struct Orig {
   double Ka(double a) const { return look1(a, P + 225, 7, P + 218); }
 };
 
+// gains folded into the CXa / dCm cells (model_simple_P indices as in SURVEY.md Appendix A)
+inline double gain_cxa(const double* P) { return P[126]; }
+inline double gain_dcm(const double* P) { return P[217] * P[150]; }
+
 struct Fast {
   std::vector<double> bM, bA, bH, bC;  // merged + extended breakpoints (alpha in degrees)
   std::vector<float> v;                // CELLS * 4 floats
@@ -145,18 +151,18 @@ inline Fast build() {
     q[3] = (float)(((t11 - t01) - (t10 - t00)) / (w0 * w1));
   };
   auto wd = [](const std::vector<double>& b, int i, double unit) { return (b[i + 1] - b[i]) / unit; };
-  auto cell_inner = [&](float* q, double t00, double t10, double t01, double t11, double w0, double w1) {
+  auto cell_inner = [&](float* q, double gain, double t00, double t10, double t01, double t11, double w0, double w1) {
     float c[4];
-    cell(c, t00, t10, t01, t11, w0, w1);
+    cell(c, gain * t00, gain * t10, gain * t01, gain * t11, w0, w1);
     q[0] = c[3]; q[1] = c[1]; q[2] = c[2]; q[3] = c[0];
   };
   for (int iM = 0; iM < NM; iM++)
     for (int iH = 0; iH < NH; iH++)
-      cell_inner(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], O.dCm(F.bH[iH], F.bM[iM]), O.dCm(F.bH[iH], F.bM[iM + 1]),
+      cell_inner(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], gain_dcm(P), O.dCm(F.bH[iH], F.bM[iM]), O.dCm(F.bH[iH], F.bM[iM + 1]),
            O.dCm(F.bH[iH + 1], F.bM[iM]), O.dCm(F.bH[iH + 1], F.bM[iM + 1]), wd(F.bM, iM, 1.0), wd(F.bH, iH, 1.0));
   for (int iC = 0; iC < NC; iC++)
     for (int iM = 0; iM < NM; iM++)
-      cell_inner(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], O.CXa(F.bM[iM], F.bC[iC]), O.CXa(F.bM[iM + 1], F.bC[iC]),
+      cell_inner(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], gain_cxa(P), O.CXa(F.bM[iM], F.bC[iC]), O.CXa(F.bM[iM + 1], F.bC[iC]),
            O.CXa(F.bM[iM], F.bC[iC + 1]), O.CXa(F.bM[iM + 1], F.bC[iC + 1]), wd(F.bM, iM, 1.0), wd(F.bC, iC, 1.0));
   for (int iA = 0; iA < NA; iA++)
     for (int iM = 0; iM < NM; iM++) {
@@ -212,8 +218,8 @@ struct FastEval {
     out[0] = bil(cy, dM, dA);
     out[3] = bil(mz, dM, dA);
     const int iC = find(F, AXC, NC, out[0]);
-    out[1] = bil_inner(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], dM, off(AXC, iC, out[0]));
-    out[2] = bil_inner(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], dM, dH);
+    out[1] = bil_inner(&F.v[(size_t)(T_MC + iC * NM + iM) * 4], dM, off(AXC, iC, out[0])) / gain_cxa(O.P);
+    out[2] = bil_inner(&F.v[(size_t)(T_HM + iM * NH + iH) * 4], dM, dH) / gain_dcm(O.P);
     const float* k = &F.v[(size_t)(AXA + iA) * 4];
     out[4] = (double)k[2] + dA * (double)k[3];
   }
