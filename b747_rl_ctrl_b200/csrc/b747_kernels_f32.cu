@@ -598,7 +598,7 @@ static int step_grid(int n) {
 }
 
 // resolve the persistent grids once, outside any stream capture (b747_create)
-void f32_warm_launch() { step_grid<0>(1 << 30); step_grid<1>(1 << 30); step_grid<2>(1 << 30); }
+void f32_warm_launch() { step_grid<0>(1 << 30); step_grid<1>(1 << 30); step_grid<2>(1 << 30); }  // occupancy is per tier (same launch bounds for every SW)
 
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s) {
@@ -610,6 +610,8 @@ void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions
     k_env_step32<0, SW_RP><<<step_grid<0>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && f32_is_lean(c))
     k_env_step32<0><<<step_grid<0>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+  else if (plain && !f32_needs_cs(c) && mp.sw == SW_RP)
+    k_env_step32<1, SW_RP><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && !f32_needs_cs(c))
     k_env_step32<1><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else

@@ -570,14 +570,15 @@ __device__ __forceinline__ void model_step32(const float4* __restrict__ sT, cons
   const float X_Vx = XXI.x, X_Vy = XVW.x, X_wz = XVW.y;
   const float a_h = aHT.x, a_th = aHT.y, a_Vy = aVW.x, a_wz = aVW.y, a_Vx = aXI.x, a_ssi = aXI.y, a_ssf = aFD.x, a_dvi = aFD.y;
   s4.h = X_h; s4.Vx = X_Vx; s4.Vy = X_Vy; s4.wz = X_wz;
-  const float h6 = (float)(kH / 6.0);
+  // y += h/6 * sum, accumulated in float64: one conversion and one DFMA per state
   const double h6d = kH / 6.0;
-  r.h += (double)(h6 * a_h); r.Vx += (double)(h6 * a_Vx); r.Vy += (double)(h6 * a_Vy); r.wz += (double)(h6 * a_wz);
-  r.ssi += (double)(h6 * a_ssi); r.ssf += (double)(h6 * a_ssf); r.th += (double)(h6 * a_th);
+  r.h = fma((double)a_h, h6d, r.h); r.Vx = fma((double)a_Vx, h6d, r.Vx); r.Vy = fma((double)a_Vy, h6d, r.Vy);
+  r.wz = fma((double)a_wz, h6d, r.wz); r.ssi = fma((double)a_ssi, h6d, r.ssi); r.ssf = fma((double)a_ssf, h6d, r.ssf);
+  r.th = fma((double)a_th, h6d, r.th);
   if (CS) { r.csi = fma(h6d, a_csi, r.csi); r.csf = fma(h6d, a_csf, r.csf); }
-  if (want_x) r.x += (double)(h6 * a_x);
-  r.dvi += (double)(h6 * a_dvi);
-  r.itse += (double)(h6 * a_itse);
+  if (want_x) r.x = fma((double)a_x, h6d, r.x);
+  r.dvi = fma((double)a_dvi, h6d, r.dvi);
+  r.itse = fma((double)a_itse, h6d, r.itse);
   r.uh[0] = r.uh[1]; r.uh[1] = r.uh[2]; r.uh[2] = r.uh[3]; r.uh[3] = u_n;
   r.tick = n + 1;
 }
