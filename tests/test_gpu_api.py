@@ -232,6 +232,30 @@ def test_step_host_pipeline_equals_one_launch(dtype_name, n):
         e.close()
 
 
+def test_explicit_oscillating_episode_on_canonical_f32_handle(oracle):
+    """b747_reset_to with an oscillating reference on a handle whose configuration family never draws one: the f32
+    launch must leave the canonical (LEAN) kernel tier -- which has no reference generator -- for the full one."""
+    from b747_rl_ctrl_b200 import engine as E
+    n = 64
+    kw = dict(sample_time=0.05, tk=3.0)
+    eng = E.BatchEngine(n_envs=n, dtype=E.F32, seed=4, auto_reset=False, **kw)
+    ob = oracle.OracleBatch(oracle.make_cfg(seed=4, **kw), n)
+    osc = ([3 * DEG, 2 * DEG, 1 * DEG], [0.05, 0.2, 0.4])
+    eps_g = [E.episode([0, 9000 + 10 * i, 230, 2, 0, 0], osc=osc) for i in range(n)]
+    eps_o = [oracle.episode([0, 9000 + 10 * i, 230, 2, 0, 0], osc=osc) for i in range(n)]
+    eng.reset_to(eps_g)
+    ob.reset_to(eps_o)
+    rng = np.random.default_rng(3)
+    for k in range(60):
+        a = rng.uniform(-1, 1, n).astype(np.float32)
+        obs, rew, done = eng.step_host(a)
+        o_o, r_o, d_o, _ = ob.step(a.astype(np.float64), auto_reset=False)
+        assert np.array_equal(done.astype(bool), d_o)
+        assert np.abs(obs - o_o).max() <= 1e-5 and np.abs(rew - r_o).max() <= 2e-3, k
+    assert np.abs(o_o[:, 1]).max() > 1e-3  # the reference really moved
+    eng.close()
+
+
 def test_step_host_graph_replay_with_pinned_buffers():
     """With pinned host buffers b747_step_host replays its pipeline as a CUDA graph (one launch call per step); results
     equal the eager pipeline's on pageable buffers, across buffer sets and across a parameter change."""
