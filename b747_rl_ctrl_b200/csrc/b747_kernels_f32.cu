@@ -244,6 +244,9 @@ __device__ __forceinline__ void load_tables32(float4* sT, const float4* __restri
 #ifndef B747_F32_MINBLOCKS
 #define B747_F32_MINBLOCKS 4
 #endif
+#ifndef B747_F32_THREADS
+#define B747_F32_THREADS 128  // threads per block of the tier-0 step kernel (tiers 1, 2: 128)
+#endif
 #ifndef B747_EXT_MINBLOCKS
 #define B747_EXT_MINBLOCKS 3
 #endif
@@ -253,7 +256,12 @@ __device__ __forceinline__ void load_tables32(float4* sT, const float4* __restri
 // TIER 0: canonical family (LEAN layout); 1: general layout without the altitude loop (other observation layouts,
 // oscillating references, aero disturbance, TF reward, signal export, trace); 2: + the altitude loop (СУ PID).
 template <int TIER, int SW = -1>
-__global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER == 1 ? B747_EXT_MINBLOCKS : B747_F32_MINBLOCKS)) k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
+#ifdef B747_F32_MAXNREG
+#define B747_STEP_BOUNDS __launch_bounds__(TIER == 0 ? B747_F32_THREADS : 128) __maxnreg__(TIER == 0 ? B747_F32_MAXNREG : 168)
+#else
+#define B747_STEP_BOUNDS __launch_bounds__(TIER == 0 ? B747_F32_THREADS : 128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER == 1 ? B747_EXT_MINBLOCKS : B747_F32_MINBLOCKS))
+#endif
+__global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                     uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
   // Persistent warps: the launch fills the GPU once (blocks = SMs x resident blocks per SM), the tables are staged into
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER ==
   __shared__ float4 sT[kFastCells];
   __shared__ double s_stats[4];
   __shared__ __align__(128) unsigned char sStage[STAGED ? 4 : 1][STAGED ? kStageBytes : 16];
-  __shared__ __align__(8) unsigned long long sBar[4];
+  __shared__ __align__(8) unsigned long long sBar[8];
   const size_t np = (size_t)c.n_pad;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
   const int n_tiles = (c.env_hi - c.env_lo + 31) >> 5;
@@ -582,7 +590,8 @@ static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 // grid of the step kernel: enough blocks to fill every SM at the kernel's occupancy, never more than the tiles need
 template <int TIER>
 static int step_grid(int n) {
-  const int need = grid_for(n, 128);
+  constexpr int threads = TIER == 0 ? B747_F32_THREADS : 128;
+  const int need = grid_for(n, threads);
   if (!B747_PERSISTENT) return need;
   static int resident[64] = {0};  // per device: SMs x blocks per SM
   int dev = 0;
@@ -591,7 +600,7 @@ static int step_grid(int n) {
   if (!resident[dev]) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step32<TIER>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step32<TIER>, threads, 0);
     resident[dev] = sms > 0 && per_sm > 0 ? sms * per_sm : need;
   }
   return need < resident[dev] ? need : resident[dev];
@@ -607,9 +616,9 @@ void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions
   if (n <= 0) return;
   const bool plain = !st.trace.trk && !st.trace.rec && !st.sig && !c.force_full;
   if (plain && f32_is_lean(c) && mp.sw == SW_RP)  // the canonical switch setting (use_RP only) as a compile-time constant
-    k_env_step32<0, SW_RP><<<step_grid<0>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    k_env_step32<0, SW_RP><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && f32_is_lean(c))
-    k_env_step32<0><<<step_grid<0>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    k_env_step32<0><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && !f32_needs_cs(c) && mp.sw == SW_RP)
     k_env_step32<1, SW_RP><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && !f32_needs_cs(c))
