@@ -92,8 +92,11 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
 // mbarrier.  The copy of tile k+1 is issued as soon as tile k has been read into registers, so the HBM latency of the
 // next tile hides behind the K model steps of the current one and the memory system always has every warp's next
 // tile in flight (ncu r1e: at K = 1 the step was latency-bound at 58 % of the HBM roof with plain loads).
-#ifndef B747_STAGED
-#define B747_STAGED 0  // measured round 1: no gain over plain 128-bit loads (K=1: 0.091 vs 0.087 ms; K=10: 0.352 vs 0.344 ms)
+// Selected per launch (launch_env_step32): on for K <= B747_STAGED_MAX_K substeps, where the step is HBM-latency bound
+// (measured round 1, 1 Mi envs: K=1 0.0737 -> 0.0715 ms), off above (K=2 0.090 vs 0.091 ms, K=10 0.283 vs 0.289 ms: the extra
+// shared-memory round trip costs issue slots the compute-bound regime does not have).
+#ifndef B747_STAGED_MAX_K
+#define B747_STAGED_MAX_K 1
 #endif
 constexpr int kStageGroups = 9, kStageBytes = kStageGroups * 512;
 
@@ -255,7 +258,7 @@ __device__ __forceinline__ void load_tables32(float4* sT, const float4* __restri
 #endif
 // TIER 0: canonical family (LEAN layout); 1: general layout without the altitude loop (other observation layouts,
 // oscillating references, aero disturbance, TF reward, signal export, trace); 2: + the altitude loop (СУ PID).
-template <int TIER, int SW = -1>
+template <int TIER, int SW = -1, bool STG = false>
 #ifdef B747_F32_MAXNREG
 #define B747_STEP_BOUNDS __launch_bounds__(TIER == 0 ? B747_F32_THREADS : 128) __maxnreg__(TIER == 0 ? B747_F32_MAXNREG : 168)
 #else
@@ -268,7 +271,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
   // shared memory once per block, and every warp then walks its own stride of 32-env tiles with no block-level
   // synchronisation until the episode statistics are flushed at the very end.
   constexpr bool GEN = TIER >= 1, CS = TIER >= 2;
-  constexpr bool STAGED = !GEN && B747_STAGED;
+  constexpr bool STAGED = !GEN && STG;
   __shared__ float4 sT[kFastCells];
   __shared__ double s_stats[4];
   __shared__ __align__(128) unsigned char sStage[STAGED ? 4 : 1][STAGED ? kStageBytes : 16];
@@ -615,7 +618,9 @@ void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions
   const int n = c.env_hi - c.env_lo;
   if (n <= 0) return;
   const bool plain = !st.trace.trk && !st.trace.rec && !st.sig && !c.force_full;
-  if (plain && f32_is_lean(c) && mp.sw == SW_RP)  // the canonical switch setting (use_RP only) as a compile-time constant
+  if (plain && f32_is_lean(c) && mp.sw == SW_RP && c.substeps <= B747_STAGED_MAX_K)  // HBM-bound regime: TMA-staged state
+    k_env_step32<0, SW_RP, true><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+  else if (plain && f32_is_lean(c) && mp.sw == SW_RP)  // the canonical switch setting (use_RP only) as a compile-time constant
     k_env_step32<0, SW_RP><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && f32_is_lean(c))
     k_env_step32<0><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);

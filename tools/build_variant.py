@@ -18,7 +18,7 @@ out_dir = os.path.join(B.LIBDIR, "variants")
 os.makedirs(out_dir, exist_ok=True)
 src = f"b747_kernels_{unit}.cu"
 obj = os.path.join(B.OBJDIR, f"{unit}_{name}.o")
-subprocess.run([B._nvcc()] + B.ARCH + B.COMMON + B.UNITS[src] + flags + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, src), "-o", obj],
+subprocess.run([B._nvcc()] + B.ARCH + B.COMMON + B.UNITS[src] + flags + (["-Xptxas", "-v"] if os.environ.get("B747_PTXAS_V") else []) + ["-c", os.path.join(B.CSRC, src), "-o", obj],
                check=True)
 other = "b747_kernels_f64.o" if unit == "f32" else "b747_kernels_f32.o"
 objs = [os.path.join(B.OBJDIR, other), obj, os.path.join(B.OBJDIR, "b747_capi.o")]
