@@ -231,6 +231,10 @@ __device__ __forceinline__ void episode_from_state_mx(const StateF32& st, size_t
   ep.osc = (r.flags & FL_OSC) != 0;
 }
 
+// exp for the reward terms: one multiply and one MUFU.EX2 (2 ulp; the rewards carry a 2e-3 bound).  Arguments are <= 0
+// except for non-finite states, where ex2 returns +inf / NaN like expf.
+__device__ __forceinline__ float exp_fast(float x) { return ex2_fast(x * 1.4426950408889634f); }
+
 __device__ __forceinline__ float nan_to_num_f(float x) {
   if (x != x) return 0.f;
   if (isinf(x)) return x > 0 ? 3.402823466e38f : -3.402823466e38f;
@@ -411,10 +415,10 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
                       kI = (float)c.rew[4], kf = (float)c.rew[5], kt = (float)c.rew[6], ko = (float)c.rew[7];
           const float inv_vf = 1.0f / vf;
           const float rel = fabsf(dv * inv_vf);
-          float r1 = 0.5f * expf(-k0 * (k1 * fabsf(dv) + k2 * fabsf(dv_dt_f) + k3 * fabsf(dv_dt_dt)) * fabsf(inv_vf));
-          float r2 = (vr * dv < 0.f) ? 0.2f * expf(-ko * rel) : 0.2f;
-          float r3 = (rel > 0.05f) ? 0.2f * expf(-kt * time) : 0.2f;
-          float r4 = 0.1f * expf(-kI * itse * inv_vf * inv_vf);
+          float r1 = 0.5f * exp_fast(-k0 * (k1 * fabsf(dv) + k2 * fabsf(dv_dt_f) + k3 * fabsf(dv_dt_dt)) * fabsf(inv_vf));
+          float r2 = (vr * dv < 0.f) ? 0.2f * exp_fast(-ko * rel) : 0.2f;
+          float r3 = (rel > 0.05f) ? 0.2f * exp_fast(-kt * time) : 0.2f;
+          float r4 = 0.1f * exp_fast(-kI * itse * inv_vf * inv_vf);
           float rf = 0.f;
           if (c.ctrl_mode == B747_MODE_DIRECT)
             rf = -kf * (0.5f * rel) * fabsf(r.deltaz - o.U_com_PID) * (float)(1.0 / (34 * kPi / 180));
