@@ -364,7 +364,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
     const float dv_dt_f = (float)dv_dt;
     const float dv_dt_dt = (dv_dt_f - r.d2_u) * 100.0f;
     const float dv = (float)o.dv;
-    const float time = (float)((double)r.tick * kH);
+    const float time = (float)r.tick * (float)kH;  // float32 product: 6e-8 relative, read by exp(-kt t) and the T?E signals only
     // Controller.vartheta_ref (core/controller.py:267-270)
     const float vr = use_ctrl ? r.sig_vzh : (float)r.vartheta;
     // observation (env/ctrl_env.py:200-247)
@@ -372,7 +372,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
     const int od = GEN ? c.obs_dim : 3;
     if (!GEN) {  // canonical layout (PID_LIKE): three scalars, no indexed array
       obs[0] = (float)s4.dvi; obs[1] = dv; obs[2] = dv_dt_f;
-      if (c.norm_obs) { obs[0] /= (float)(60 * kPi); obs[1] /= (float)kPi; obs[2] /= (float)kPi; }
+      if (c.norm_obs) { obs[0] *= (float)(1.0 / (60 * kPi)); obs[1] *= (float)(1.0 / kPi); obs[2] *= (float)(1.0 / kPi); }
     } else {
       const float pi = (float)kPi;
       if (c.obs_type == B747_OBS_MODEL_STATE) {
