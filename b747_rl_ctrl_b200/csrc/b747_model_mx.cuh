@@ -20,14 +20,18 @@
 //    bilinear interpolant) and stored as polynomial coefficients in the offsets from the interval's lower
 //    breakpoint.  The current interval {bp, width} of every axis and the coefficients of the current cells
 //    live in REGISTERS (TabCache); a pass validates them with one unsigned compare per axis and evaluates
-//    each table with three FMAs.  Shared memory is touched only when an operand crossed a breakpoint (Mach,
-//    alpha and h move by ~1e-4 of an interval per pass; CYa crosses its 0.1-wide intervals more often): the
-//    refill walks to the neighbour interval and reloads the cells it addresses.  (ncu r1d: the per-pass LDS.128
-//    validation of the previous design drew 40 % of the kernel's stall samples and 72 % of the
-//    shared-memory wavefront peak.)
+//    the tables with packed FFMA2 (CYa + mz as coefficient pairs, the inner terms of CXa / dCm as pairs).  Shared
+//    memory is touched only when an operand crossed a breakpoint (about once per model step and warp: CYa and
+//    alpha cross their 0.1 / 0.6-deg intervals): the CYa walk is inline, the alpha-only and the full refill are
+//    out-of-line functions (ncu r1d: the per-pass LDS.128 validation of the previous design drew 40 % of
+//    the kernel's stall samples and 72 % of the shared-memory wavefront peak);
 //  * sin/cos(theta), atan(wb/ub) and the ISA density power are short float32 polynomials
 //    (b747_poly.h, generated + validated by tools/gen_poly.py) with libm fall-backs outside their
-//    fitted ranges; sin(alpha), cos(alpha) come from the body-axis velocity components;
+//    fitted ranges, evaluated at the major pass only: the three RK stages advance sin/cos by a rotation
+//    and alpha by the asin of the normalised cross product of the body-velocity vectors (TrigMx), the
+//    atmosphere by its derivative in h (AtmoMx); sin(alpha), cos(alpha) come from the body-axis velocity
+//    components;
+//  * the RK4 bookkeeping runs on register pairs with packed FFMA2, the weights as broadcast scalars;
 //  * the transport delay (0.03 s = 3 steps), the Derivative and rate-limiter stamps are resolved
 //    from the integer tick, so no time-stamp arithmetic is left in floating point;
 //  * states that no observation/reward reads (ITAE, IAE, ISE; x and the altitude-loop PID unless the
