@@ -420,13 +420,15 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
   else td = n >= 3 ? 0.5f * (r.uh[1] + r.uh[2]) : PCF(137);
   o.td = td;
   if (major && (n % 5) == 0) r.df_y = fmaf(r.df_x, PCF(140), PCF(141) * td);
-  float yv = r.df_y;
-  if (!(major && n == 0)) {
-    const float dT = (stage == 1 || stage == 2) ? 0.005f : 0.01f;
-    yv = r.rl_prev + fminf(fmaxf(yv - r.rl_prev, dT * PCF(143)), dT * PCF(142));
+  if (stage != 2) {  // the second half-step pass sees the same filter output, memory and dT as the first: o keeps its values
+    float yv = r.df_y;
+    if (!(major && n == 0)) {
+      const float dT = stage == 1 ? 0.005f : 0.01f;
+      yv = r.rl_prev + fminf(fmaxf(yv - r.rl_prev, dT * PCF(143)), dT * PCF(142));
+    }
+    o.rl_out = yv;
+    o.deltaz_RP = satf(yv, PCF(145), PCF(144));
   }
-  o.rl_out = yv;
-  o.deltaz_RP = satf(yv, PCF(145), PCF(144));
   // СУ PID (altitude loop) -- only integrated when the configuration can close it.  Its output is the
   // pitch reference, which the СС PID differentiates with a gain of Kd*N ~ 390, so the whole
   // altitude-error chain is float64 (a float32 altitude quantises it at ~1e-5 rad).
