@@ -1,7 +1,7 @@
 #!/bin/bash
 # SASS opcode histogram of the K loop (largest backward branch) of k_env_step32<false>; usage: tools/loop_hist.sh obj
 obj=${1:-b747_rl_ctrl_b200/build/b747_kernels_f32.o}
-cuobjdump -sass -fun '_ZN4b74712k_env_step32ILi0ELi4EEEvNS_6DevCfgENS_4MP32ENS_8StateF32EPKfPfS6_PhS6_' $obj > /tmp/loop.sass
+cuobjdump -sass -fun '_ZN4b74712k_env_step32ILi0ELi4ELb0EEEvNS_6DevCfgENS_4MP32ENS_8StateF32EPKfPfS6_PhS6_' $obj > /tmp/loop.sass
 python3 - <<'PY'
 import re,collections
 L=[l for l in open('/tmp/loop.sass') if re.match(r'\s+/\*[0-9a-f]{4}\*/',l)]

@@ -44,7 +44,7 @@ for f in sorted(os.listdir(tmp)):
         if m:
             if infn and fn_lines:
                 break
-            infn = want in m.group(1) and "<false>" not in ln and ("ILi0ELi4" in m.group(1) or "ILb0" in m.group(1))
+            infn = want in m.group(1) and "<false>" not in ln and ("ILi0ELi4ELb0" in m.group(1) or "ILb0EEE" in m.group(1))
             fn_lines = []
             continue
         if not infn:
