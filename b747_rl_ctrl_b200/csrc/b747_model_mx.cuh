@@ -284,7 +284,7 @@ struct AtmoMx { float h0, rho0, ia0, s_rho, s_ia; };
 // rad even for a tumbling airframe), so sin/cos follow by a rotation with short series for sin/cos(delta), and alpha by
 // the angle between the body-velocity vectors of the two passes (asin of their normalised cross product).  Both are
 // more accurate than re-evaluating the float32 polynomials (no argument rounding), and need no range checks.
-struct TrigMx { float sn, cs, thf, sgn, ub, wb, rV, alpha; double thd; };
+struct TrigMx { float2 sc, cn; float thf, sgn, ub, wb, rV, alpha; double thd; };  // sc = (sin, cos), cn = (cos, -sin) of the major pass
 
 // One pass over the diagram at a stage state.  stage: 0 major, 1/2 half steps, 3 full step.
 // Passes 0 and 3 -- the ones whose pitch error is differenced by the Derivative blocks, observed and rewarded -- carry
@@ -328,7 +328,7 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
     float pc = fmaf(poly::COS4, z, poly::COS3); pc = fmaf(pc, z, poly::COS2); pc = fmaf(pc, z, poly::COS1); pc = fmaf(pc, z, poly::COS0);
     sn = fmaf(thf * z, ps, thf);
     cs = fmaf(z, pc, 1.0f);
-    tg.sn = sn; tg.cs = cs; tg.thf = thf; tg.thd = th_fold;
+    tg.sc = make_float2(sn, cs); tg.cn = make_float2(cs, -sn); tg.thf = thf; tg.thd = th_fold;
   } else {
     // increment of the folded pitch since the major pass: exact difference at the full step (the fold is continuous),
     // sgn * wz * h/2 at the half steps
@@ -342,8 +342,12 @@ __device__ __forceinline__ void pass32(const float4* __restrict__ sT, const MP32
     const float d2 = dl * dl;
     const float sd = fmaf(dl * d2, fmaf(d2, 8.33333333e-3f, -0.166666667f), dl);
     const float cd = fmaf(d2, fmaf(d2, 4.16666667e-2f, -0.5f), 1.0f);
-    sn = fmaf(tg.sn, cd, tg.cs * sd);
-    cs = fabsf(fmaf(tg.cs, cd, -tg.sn * sd));  // the folded pitch stays within +-90 deg: cos >= 0 (a half step may cross the fold)
+    // (sin, cos)(theta0 + dl) = (sin, cos) cd + (cos, -sin) sd: one packed multiply and one packed FMA
+    const float2 cdd = make_float2(cd, cd), sdd = make_float2(sd, sd);
+    const float2 t = B747_PAIR_RK ? __fmul2_rn(tg.cn, sdd) : make_float2(tg.cn.x * sd, tg.cn.y * sd);
+    const float2 rot = fma2(tg.sc, cdd, t, B747_PAIR_RK);
+    sn = rot.x;
+    cs = fabsf(rot.y);  // the folded pitch stays within +-90 deg: cos >= 0 (a half step may cross the fold)
   }
   o.th = thf;
   o.thd = th_fold;
