@@ -13,9 +13,9 @@
 // 144 B in + 144 B out per env step, plus action (4) obs (12) reward (4) done (1) = 309 B/env-step,
 // independent of K.
 //
-// Three instantiations of the step kernel (launch_env_step32 picks one per handle): tier 0 the canonical family on the
-// LEAN layout, tier 1 the general layout without the altitude loop, tier 2 everything (altitude loop, recorder / tracker,
-// signal export).  All are persistent-warp kernels: grid = SMs x resident blocks, tables staged once per block.
+// Instantiations of the step kernel (launch_env_step32 picks one per handle): tier 0 the canonical family on the LEAN
+// layout, tier 1 the general layout without the altitude loop, tier 2 with it, tier 3 with recorder / tracker / signal
+// export as well (each feature left out of a tier is left out of its instruction footprint).  All are persistent-warp kernels: grid = SMs x resident blocks, tables staged once per block.
 #include <string.h>
 
 #include <vector>
@@ -261,12 +261,12 @@ __device__ __forceinline__ void load_tables32(float4* sT, const float4* __restri
 #define B747_GEN_MINBLOCKS 3  // measured: 168 registers x 12 warps beats 242 x 8 (0.66 -> 0.52 ms per 1 Mi-env K=10 step)
 #endif
 // TIER 0: canonical family (LEAN layout); 1: general layout without the altitude loop (other observation layouts,
-// oscillating references, aero disturbance, TF reward, signal export, trace); 2: + the altitude loop (СУ PID).
+// oscillating references, aero disturbance, TF reward); 2: + the altitude loop (СУ PID); 3: + recorder, tracker, signal export.
 template <int TIER, int SW = -1, bool STG = false>
 #ifdef B747_F32_MAXNREG
 #define B747_STEP_BOUNDS __launch_bounds__(TIER == 0 ? B747_F32_THREADS : 128) __maxnreg__(TIER == 0 ? B747_F32_MAXNREG : 168)
 #else
-#define B747_STEP_BOUNDS __launch_bounds__(TIER == 0 ? B747_F32_THREADS : 128, TIER == 2 ? B747_GEN_MINBLOCKS : (TIER == 1 ? B747_EXT_MINBLOCKS : B747_F32_MINBLOCKS))
+#define B747_STEP_BOUNDS __launch_bounds__(TIER == 0 ? B747_F32_THREADS : 128, TIER >= 2 ? B747_GEN_MINBLOCKS : (TIER == 1 ? B747_EXT_MINBLOCKS : B747_F32_MINBLOCKS))
 #endif
 __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
@@ -274,7 +274,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
   // Persistent warps: the launch fills the GPU once (blocks = SMs x resident blocks per SM), the tables are staged into
   // shared memory once per block, and every warp then walks its own stride of 32-env tiles with no block-level
   // synchronisation until the episode statistics are flushed at the very end.
-  constexpr bool GEN = TIER >= 1, CS = TIER >= 2;
+  constexpr bool GEN = TIER >= 1, CS = TIER >= 2, TRACE = TIER >= 3;
   constexpr bool STAGED = !GEN && STG;
   __shared__ float4 sT[kFastCells];
   __shared__ double s_stats[4];
@@ -345,12 +345,12 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
     }
     PassMx o;
     Stage4Mx s4;
-    const bool tracing = CS && (st.trace.trk || st.trace.rec);  // recorder / tracker / signal export: tier 2 only
+    const bool tracing = TRACE && (st.trace.trk || st.trace.rec);  // recorder / tracker / signal export: tier 3 only
     const bool want_x = GEN && (c.obs_type == B747_OBS_MODEL_STATE || tracing);
 #pragma unroll 1
     for (int k = 0; k < c.substeps; k++) {
       model_step32<TIER, SW>(sT, mp, c, r, o, s4, want_x);
-      if (CS && tracing) {  // Controller._post_step (core/controller.py:209-228)
+      if (TRACE && tracing) {  // Controller._post_step (core/controller.py:209-228)
         TraceSample ts;
         ts.t = (double)r.tick * kH; ts.U_com = o.U_com; ts.U_PID = o.U_com_PID; ts.deltaz_RP = o.deltaz_RP;
         ts.hzh = r.href; ts.vref = use_ctrl ? (double)o.vartheta_zh : r.vartheta; ts.U_RL = a;
@@ -399,7 +399,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
           for (int k = 0; k < n; k++) obs[k] /= mx[k];
       }
     }
-    if (CS && st.trace.trk) {  // Controller.quality of the running episode
+    if (TRACE && st.trace.trk) {  // Controller.quality of the running episode
       const double q = exp(-60 * 0.1 * s4.itse / (c.tk * ((double)vr * (double)vr)));
       st.trace.trk[(size_t)TRK_quality * np + i] = q;
       st.trace.trk[((size_t)NTRK + TRK_quality) * np + i] = q;
@@ -444,7 +444,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
     done = (int64_t)r.tick >= c.done_tick;
     if (c.use_limiter && (fabsf(nan_to_num_f(o.th)) > (float)(5 * kPi / 180 + c.vartheta_max) || r.deltaz > (float)c.action_max))
       done = true;
-    if (CS && st.sig) {  // signal export: full tier only (launch_env_step32)
+    if (TRACE && st.sig) {  // signal export: full tier only (launch_env_step32)
       float* sg = st.sig;
 #define SG(name, v) sg[(size_t)SIG_##name * np + i] = (v)
       const float qn = nanf("");
@@ -465,16 +465,16 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
     if (done) {
       ep_ret = r.ep_return; ep_len = (double)(r.tick / c.substeps);
       st.last_ret[i] = ep_ret; st.last_len[i] = r.tick / c.substeps;
-      if (CS && st.trace.trk) trace_snapshot(st.trace, np, i, st.trace.trk[(size_t)TRK_quality * np + i]);
+      if (TRACE && st.trace.trk) trace_snapshot(st.trace, np, i, st.trace.trk[(size_t)TRK_quality * np + i]);
       if (c.auto_reset) {
-        if (CS) trace_clear(st.trace, np, i);
+        if (TRACE) trace_clear(st.trace, np, i);
         Episode ep;
         if (c.reset_ref_mode == B747_RESET_NONE) episode_from_state_mx(st, np, i, r, ep);
         else { draw_episode(c, (uint64_t)(c.env_id_offset + i), r.ep_idx, ep); r.ep_idx++; }
         env_reset_mx<GEN>(c, ep, r, st, np, i);
         full_store = true;
         for (int k = 0; k < od; k++) obs[k] = 0.f;
-        if (CS && st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
+        if (TRACE && st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
       }
     }
     if (od == 3) {  // canonical layout: three contiguous floats per env
@@ -614,7 +614,7 @@ static int step_grid(int n) {
 }
 
 // resolve the persistent grids once, outside any stream capture (b747_create)
-void f32_warm_launch() { step_grid<0>(1 << 30); step_grid<1>(1 << 30); step_grid<2>(1 << 30); }  // occupancy is per tier (same launch bounds for every SW)
+void f32_warm_launch() { step_grid<0>(1 << 30); step_grid<1>(1 << 30); step_grid<2>(1 << 30); step_grid<3>(1 << 30); }  // occupancy is per tier (same launch bounds for every SW)
 
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
                        float* term_obs, cudaStream_t s) {
@@ -632,8 +632,10 @@ void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions
     k_env_step32<1, SW_RP><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
   else if (plain && !f32_needs_cs(c))
     k_env_step32<1><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
-  else
+  else if (plain)
     k_env_step32<2><<<step_grid<2>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+  else
+    k_env_step32<3><<<step_grid<3>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
 }
 void launch_reset32(const DevCfg& c, const StateF32& st, const uint8_t* mask, const b747_episode* eps, float* obs,
                     cudaStream_t s) {
