@@ -29,6 +29,7 @@ struct Regs64 {
   int tick, flags;
   uint32_t ep_idx;
   double use_PID_CS;  // per env (HYBRID toggles it per episode); derived from flags
+  unsigned long long lut = 0;  // last interval of the nine prelookups, 4 bits each (registers only; always re-validated)
 };
 
 enum { IX_x = 0, IX_h, IX_q0, IX_q3, IX_Vx, IX_Vy, IX_wz, IX_csi, IX_csf, IX_ssi, IX_ssf, IX_dvi, IX_itae, IX_iae, IX_ise, IX_itse };
@@ -70,11 +71,31 @@ __device__ __forceinline__ unsigned prelookup64(double u, const double* bp, unsi
   return iLeft;
 }
 
+// The same prelookup with the previous interval as a hint: the operands move by a small fraction of an interval per
+// pass, so the DLL's binary search almost always lands where it landed last time.  The hint is checked against the
+// search's own postcondition (u <= bp[0] -> 0; u >= bp[max] -> max-1; else bp[i] <= u < bp[i+1]) and the fraction uses
+// the same expression, so index and fraction are bit-identical to prelookup64 -- only the search is skipped.
+template <int SLOT>
+__device__ __forceinline__ unsigned prelookup64c(double u, const double* bp, unsigned maxIndex, double& frac,
+                                                 unsigned long long& lut) {
+  unsigned i = (unsigned)(lut >> (4 * SLOT)) & 15u;
+  if (i > maxIndex - 1) i = maxIndex - 1;
+  const double lo = bp[i], hi = bp[i + 1];
+  if ((i == 0 || u >= lo) && (i == maxIndex - 1 || u < hi)) {
+    frac = (u - lo) / (hi - lo);
+    return i;
+  }
+  i = prelookup64(u, bp, maxIndex, frac);
+  lut = (lut & ~(15ull << (4 * SLOT))) | ((unsigned long long)i << (4 * SLOT));
+  return i;
+}
+
+template <int SLOT>
 __device__ __forceinline__ double look2_64(double u0, double u1, const double* bp0, const double* bp1, const double* tab,
-                                           unsigned max0, unsigned max1, unsigned stride) {
+                                           unsigned max0, unsigned max1, unsigned stride, unsigned long long& lut) {
   double f0, f1;
-  unsigned i0 = prelookup64(u0, bp0, max0, f0);
-  unsigned i1 = prelookup64(u1, bp1, max1, f1);
+  unsigned i0 = prelookup64c<SLOT>(u0, bp0, max0, f0, lut);
+  unsigned i1 = prelookup64c<SLOT + 1>(u1, bp1, max1, f1, lut);
   unsigned o = i1 * stride + i0;
   double yL = (tab[o + 1] - tab[o]) * f0 + tab[o];
   o += stride;
@@ -159,8 +180,8 @@ __device__ __forceinline__ void pass64(const double* __restrict__ P, const Model
   double Mach = V / asnd;
   o.Mach = Mach;
   if (major) { hd.sumA[1] = r.aerr[1] + P[51]; hd.sumA[0] = r.aerr[0] + P[51]; }
-  double CYa = look2_64(Mach, ad, P + 42, P + 46, P + 22, 3, 4, 4) * hd.sumA[1];
-  double CXa = look2_64(Mach, CYa, P + 108, P + 112, P + 52, 3, 13, 4) * hd.sumA[0];
+  double CYa = look2_64<0>(Mach, ad, P + 42, P + 46, P + 22, 3, 4, 4, r.lut) * hd.sumA[1];
+  double CXa = look2_64<2>(Mach, CYa, P + 108, P + 112, P + 52, 3, 13, 4, r.lut) * hd.sumA[0];
   o.CYa = CYa; o.CXa = CXa;
   double Tr = T * P[127];
   double pw = (Tr < 0.0 && P[128] > floor(P[128])) ? -rt_pow_64(-Tr, P[128]) : rt_pow_64(Tr, P[128]);
@@ -201,14 +222,14 @@ __device__ __forceinline__ void pass64(const double* __restrict__ P, const Model
   if (mp.use_RL >= P[148]) o.U_com = P[147] > fabs(0.0 - o.U_com_PID) ? 0.0 : o.U_com_PID;
   else o.U_com = mp.use_PID_SS >= P[9] ? o.U_com_PID : r.deltaz;
   if (major) { hd.sumA[3] = r.aerr[3] + P[216]; hd.sumA[4] = r.aerr[4] + P[216]; }
-  o.dCm = look2_64(h, Mach, P + 201, P + 206, P + 151, 4, 9, 5) * hd.sumA[3];
+  o.dCm = look2_64<4>(h, Mach, P + 201, P + 206, P + 151, 4, 9, 5, r.lut) * hd.sumA[3];
   {
     double f;
-    unsigned i = prelookup64(ad, P + 225, 6, f);
+    unsigned i = prelookup64c<6>(ad, P + 225, 6, f, r.lut);
     o.K_alpha = ((P[218 + i + 1] - P[218 + i]) * f + P[218 + i]) * hd.sumA[4];
   }
   if (major) hd.sumA[2] = r.aerr[2] + P[216];
-  o.mz = look2_64(Mach, ad, P + 276, P + 280, P + 232, 3, 10, 4) * hd.sumA[2];
+  o.mz = look2_64<7>(Mach, ad, P + 276, P + 280, P + 232, 3, 10, 4, r.lut) * hd.sumA[2];
   double ax = (Fx * cs - sn * Fy) / mp.m0;
   double ay = (Fy * cs + Fx * sn) / mp.m0 - mp.g;
   double dze = mp.use_RP >= P[149] ? o.deltaz_RP : o.U_com;
