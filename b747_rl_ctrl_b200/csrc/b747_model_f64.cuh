@@ -158,7 +158,8 @@ __device__ __forceinline__ void pass64(const double* __restrict__ P, const Model
   double q3 = Xs[IX_q3] / nq, q0 = Xs[IX_q0] / nq;
   double th = asin((0.0 + q3 * q0) * 2.0);
   o.th = th;
-  double sn = sin(th), cs = cos(th);
+  double sn, cs;
+  sincos(th, &sn, &cs);  // one argument reduction for both (same values as sin / cos)
   double Vx = Xs[IX_Vx], Vy = Xs[IX_Vy];
   double ub = cs * Vx + sn * Vy;
   double wb = cs * Vy - sn * Vx;
@@ -190,7 +191,8 @@ __device__ __forceinline__ void pass64(const double* __restrict__ P, const Model
   double rho = pw / Tr * P[129] * exp(xs * P[133] * (1.0 / T));
   double rV2 = rho * (V * V);
   double qS = rV2 * P[134] * mp.S;
-  double sa = sin(alpha), ca = cos(alpha);
+  double sa, ca;
+  sincos(alpha, &sa, &ca);
   double mD = P[126] * CXa * qS;
   double Lf = qS * CYa;
   double Fx = mD * ca + sa * Lf + mp.P;
