@@ -71,9 +71,14 @@ def load():
     L.b747_set_stream.argtypes = [vp, vp]
     L.b747_reset.argtypes = [vp, vp, vp]
     L.b747_reset_to.argtypes = [vp, ctypes.POINTER(Episode), vp]
+    L.b747_reset_to_masked.argtypes = [vp, ctypes.POINTER(Episode), vp, vp]
     L.b747_step.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b747_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b747_set_host_chunks.argtypes = [vp, c_int]
+    L.b747_step_packed.argtypes = [vp, vp, vp, vp]
+    L.b747_step_host_packed.argtypes = [vp, vp, vp, vp]
+    L.b747_set_host_mode.argtypes = [vp, c_int]
+    L.b747_set_seed.argtypes = [vp, ctypes.c_uint64]
     L.b747_model_step.argtypes = [vp, ctypes.c_int32]
     L.b747_model_initialize.argtypes = [vp]
     L.b747_set_param.argtypes = [vp, ctypes.c_char_p, c_dp, c_int]

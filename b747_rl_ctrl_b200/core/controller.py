@@ -40,15 +40,19 @@ class DisturbanceMode(Enum):  # core/controller.py:34-36
     AERO_DISTURBANCE = 0
 
 
-def _const_value(func, what):
-    """The kernels hold the reference constant over an episode (or use the built-in 3-sine reference);
-    arbitrary time functions of the reference API are only accepted when they are constant."""
+def _const_value(func, what, require=False):
+    """The constant a reference function returns, or None if it varies with time.  The batched kernels hold the
+    reference constant over an episode (or use the built-in 3-sine reference); a time-varying function is evaluated on
+    the host before every env step by the single-env Controller (core/controller.py:233-239 does the same: it writes
+    func(model.time) into the model before the K substeps).  require=True (vectorised views): constants only."""
     if func is None:
         return None
     a, b, c = func(0.0), func(1.2345), func(17.0)
     if not (a == b == c):
-        raise NotImplementedError(f"{what}: only constant reference functions run in-kernel "
-                                  "(use ResetRefMode.OSCILLATING for the 3-sine reference)")
+        if require:
+            raise NotImplementedError(f"{what}: only constant reference functions run in-kernel "
+                                      "(use ResetRefMode.OSCILLATING for the 3-sine reference)")
+        return None
     return float(a)
 
 
@@ -74,6 +78,9 @@ class Controller:
         self.tk = tk
         self._h_func = h_func
         self._vartheta_func = vartheta_func
+        # time-varying reference functions are evaluated on the host before every env step (step())
+        self._vf_dynamic = vartheta_func is not None and _const_value(vartheta_func, "vartheta_func") is None
+        self._hf_dynamic = h_func is not None and _const_value(h_func, "h_func") is None
         self.action_max = action_max
         self.vartheta_max = vartheta_max
         self.use_limiter = use_limiter
@@ -110,6 +117,7 @@ class Controller:
     def vartheta_func(self, f):
         self._vartheta_func = f
         v = _const_value(f, "vartheta_func")
+        self._vf_dynamic = f is not None and v is None
         if v is not None:
             self._engine.set("vref", v)
 
@@ -121,6 +129,7 @@ class Controller:
     def h_func(self, f):
         self._h_func = f
         v = _const_value(f, "h_func")
+        self._hf_dynamic = f is not None and v is None
         if v is not None:
             self._engine.set("href", v)
 
@@ -151,16 +160,27 @@ class Controller:
             eng.reset()
         else:
             s0 = self._state0 if self._state0 is not None else self.model.state0
-            vref = _const_value(self._vartheta_func, "vartheta_func") or 0.0
-            href = _const_value(self._h_func, "h_func")
-            ep = E.episode(s0, vref=vref, h_ref=(href if href is not None else 11000.0), use_ctrl=self.use_ctrl,
-                           aero_err=self.aero_err)
+            # a time-varying function is written before every step; the episode starts from its value at t = 0
+            vref = (self._vartheta_func(0.0) if self._vf_dynamic else _const_value(self._vartheta_func, "vartheta_func")) or 0.0
+            href = self._h_func(0.0) if self._hf_dynamic else _const_value(self._h_func, "h_func")
+            aero_err = self.aero_err
+            if self.disturbance_mode == DisturbanceMode.AERO_DISTURBANCE and aero_err is None:
+                # core/controller.py:181-191: a fresh Gaussian error on every reset, drawn from numpy's global stream
+                # in the reference's order (ControllerEnv.__init__ seeds it with np.random.seed(0))
+                aero_err = np.array([np.random.normal(m, 0.5, size=None) for m in (-0.1, 0.1, -0.1, -0.1, 0.1)])
+            ep = E.episode(s0, vref=float(vref), h_ref=(float(href) if href is not None else 11000.0), use_ctrl=self.use_ctrl,
+                           aero_err=aero_err)
             eng.reset_to([ep])
         self._last = None
 
     def step(self, action=None):
         """core/controller.py:231-264: one kernel launch = reference + action law + K model steps."""
         self.state_backup = self.model.state
+        # core/controller.py:233-239: the reference is a function of model.time, written before the K substeps
+        if self._vf_dynamic and not self.use_ctrl:
+            self._engine.set("vref", float(self._vartheta_func(self.model.time)))
+        if self._hf_dynamic and self.use_ctrl:
+            self._engine.set("href", float(self._h_func(self.model.time)))
         a = 0.0
         if action is not None and len(action) > 0:
             a = float(action[-1])

@@ -33,6 +33,9 @@ struct b747_handle {
   // staging for b747_step_host
   void *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_term = nullptr;
   uint8_t* d_done = nullptr;
+  float4* d_out4 = nullptr;      // packed outputs of b747_step_host_packed (pageable / copy modes), allocated on first use
+  uint32_t* d_bits = nullptr;    // done flags, one bit per env
+  int host_mode = -1;            // b747_step_host_packed: -1 automatic, 0 copy pipeline, 1 zero-copy outputs, 2 zero-copy both ways
   // b747_step_host pipeline: copy-in / second compute / copy-out streams and per-chunk events (created on first use)
   cudaStream_t s_in = nullptr, s_aux = nullptr, s_out = nullptr, s_cap = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_k;
@@ -160,6 +163,8 @@ static int fill_devcfg(const b747_cfg& c, DevCfg& d) {
   return 0;
 }
 
+static int create_body(b747_handle* h, const b747_cfg* cfg);
+
 extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
   if (!cfg || !out) return fail(B747_ERR_ARG, "null argument");
   if (cfg->abi_version != B747_ABI_VERSION) return fail(B747_ERR_ARG, "abi_version mismatch");
@@ -184,9 +189,24 @@ extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
                                    " (libb747_b200 has no CPU path)");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(B747_ERR_ARG, "device ordinal out of range");
   CU(cudaSetDevice(cfg->device));
+  if (cfg->record_capacity > 0 &&
+      sizeof(double) * (size_t)cfg->record_capacity * NREC * (size_t)cfg->n_envs > ((size_t)8 << 30))
+    return fail(B747_ERR_ALLOC, "recorder larger than 8 GiB: lower record_capacity or n_envs");
   b747_handle* h = new b747_handle();
   h->cfg = *cfg;
   fill_devcfg(*cfg, h->dc);
+  // every failure below releases the handle and whatever it allocated so far (a retry with fewer envs finds the HBM free)
+  const int rc = create_body(h, cfg);
+  if (rc != B747_OK) {
+    const std::string msg = g_err;
+    b747_destroy(h);
+    return fail(rc, msg);
+  }
+  *out = h;
+  return B747_OK;
+}
+
+static int create_body(b747_handle* h, const b747_cfg* cfg) {
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   const size_t np = (size_t)h->dc.n_pad;
@@ -200,7 +220,6 @@ extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
   }
   if (cfg->record_capacity > 0) {
     const size_t bytes = sizeof(double) * (size_t)cfg->record_capacity * NREC * (size_t)cfg->n_envs;
-    if (bytes > ((size_t)8 << 30)) return fail(B747_ERR_ALLOC, "recorder larger than 8 GiB: lower record_capacity or n_envs");
     CU(cudaMalloc(&h->trace.rec, bytes));
     CU(cudaMemsetAsync(h->trace.rec, 0, bytes, h->stream));
     h->trace.rec_cap = cfg->record_capacity;
@@ -237,21 +256,21 @@ extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
   CU(cudaMalloc(&h->d_eps, sizeof(b747_episode) * np));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
-  *out = h;
   return B747_OK;
 }
 
 extern "C" int b747_destroy(b747_handle* h) {
   if (!h) return B747_OK;
   cudaSetDevice(h->cfg.device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream || !h->own_stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_out4); cudaFree(h->d_bits);
   cudaFree(h->trace.trk); cudaFree(h->trace.snap); cudaFree(h->trace.rec); cudaFree(h->d_metrics);
   StateF64& s = h->s64;
   cudaFree(s.slots); cudaFree(s.tick); cudaFree(s.flags); cudaFree(s.ep_idx); cudaFree(s.sig); cudaFree(s.stats);
   cudaFree(s.last_ret); cudaFree(s.last_len);
   f32_free(h->s32);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_done); cudaFree(h->d_eps);
-  if (h->own_stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_k) cudaEventDestroy(e);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -330,7 +349,7 @@ extern "C" int b747_reset(b747_handle* h, const uint8_t* mask_dev, void* obs_dev
   return B747_OK;
 }
 
-extern "C" int b747_reset_to(b747_handle* h, const b747_episode* eps, void* obs_dev) {
+extern "C" int b747_reset_to_masked(b747_handle* h, const b747_episode* eps, const uint8_t* mask_dev, void* obs_dev) {
   if (!h || !eps) return fail(B747_ERR_ARG, "null argument");
   CU(cudaSetDevice(h->cfg.device));
   // explicit episodes can ask for what the handle's configuration family never produces (closed altitude loop,
@@ -342,12 +361,16 @@ extern "C" int b747_reset_to(b747_handle* h, const b747_episode* eps, void* obs_
     if (special) { h->dc.force_full = 1; h->epoch++; }
   }
   CU(cudaMemcpyAsync(h->d_eps, eps, sizeof(b747_episode) * h->cfg.n_envs, cudaMemcpyHostToDevice, h->stream));
-  if (h->cfg.dtype == B747_F64) launch_reset64(h->dc, h->s64, nullptr, h->d_eps, (double*)obs_dev, h->stream);
-  else launch_reset32(h->dc, h->s32, nullptr, h->d_eps, (float*)obs_dev, h->stream);
+  if (h->cfg.dtype == B747_F64) launch_reset64(h->dc, h->s64, mask_dev, h->d_eps, (double*)obs_dev, h->stream);
+  else launch_reset32(h->dc, h->s32, mask_dev, h->d_eps, (float*)obs_dev, h->stream);
   h->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));  // eps is caller memory
   return B747_OK;
+}
+
+extern "C" int b747_reset_to(b747_handle* h, const b747_episode* eps, void* obs_dev) {
+  return b747_reset_to_masked(h, eps, nullptr, obs_dev);
 }
 
 extern "C" int b747_step(b747_handle* h, const void* act, void* obs, void* rew, uint8_t* done, void* term) {
@@ -496,6 +519,136 @@ extern "C" int b747_step_host(b747_handle* h, const void* act, void* obs, void* 
   const int rc = issue_pipeline(h, h->stream, act, obs, rew, done, term, chunks, per);
   if (rc != B747_OK) return rc;
   CU(cudaStreamSynchronize(h->stream));
+  return B747_OK;
+}
+
+// ---- packed outputs ------------------------------------------------------------------------------
+// One float4 per env (obs[3] before any auto-reset, reward) + one done bit per env: what the SB3-facing VecEnv needs from a
+// step, in ONE 128-bit store per thread and one ballot word per warp.  Observation layouts of three scalars only.
+static int packed_ok(b747_handle* h) {
+  if (h->cfg.dtype != B747_F32) return fail(B747_ERR_STATE, "packed outputs need an f32 handle");
+  if (h->dc.obs_dim != 3) return fail(B747_ERR_STATE, "packed outputs need a 3-scalar observation layout (PID_LIKE)");
+  if (!h->cfg.env_layer) return fail(B747_ERR_STATE, "handle was created with env_layer=0; use b747_model_step");
+  return B747_OK;
+}
+
+extern "C" int b747_step_packed(b747_handle* h, const float* act_dev, float* out4_dev, uint32_t* done_bits_dev) {
+  if (!h || !act_dev || !out4_dev || !done_bits_dev) return fail(B747_ERR_ARG, "null argument");
+  const int rc = packed_ok(h);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->cfg.device));
+  launch_env_step32(h->dc, h->s32, act_dev, nullptr, nullptr, nullptr, nullptr, h->stream, (float4*)out4_dev, done_bits_dev);
+  h->launches++;
+  CU(cudaGetLastError());
+  return B747_OK;
+}
+
+extern "C" int b747_set_host_mode(b747_handle* h, int mode) {
+  if (!h || mode < -1 || mode > 2) return fail(B747_ERR_ARG, "mode must be -1 (automatic), 0, 1 or 2");
+  h->host_mode = mode;
+  return B747_OK;
+}
+
+// device alias of a pinned (mapped) host pointer; nullptr if the memory is not device-accessible
+static void* mapped_ptr(const void* p) {
+  if (!is_pinned(p)) return nullptr;
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, (void*)p, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return d;
+}
+
+extern "C" int b747_step_host_packed(b747_handle* h, const float* act, float* out4, uint32_t* done_bits) {
+  if (!h || !act || !out4 || !done_bits) return fail(B747_ERR_ARG, "null argument");
+  const int prc = packed_ok(h);
+  if (prc) return prc;
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->cfg.n_envs, np = (size_t)h->dc.n_pad, nw = (n + 31) / 32;
+  if (!h->d_bits) CU(cudaMalloc(&h->d_bits, sizeof(uint32_t) * (np / 32)));
+  float* m_act = (float*)mapped_ptr(act);
+  float4* m_out = (float4*)mapped_ptr(out4);
+  int mode = h->host_mode;
+  if (mode < 0) mode = 2;
+  if (!m_out || !is_pinned(done_bits)) mode = 0;
+  if (mode == 2 && !m_act) mode = 1;
+  if (mode >= 1) {
+    // Zero-copy: the kernel stores each env's float4 straight into the caller's pinned buffer -- 512 contiguous bytes per
+    // warp, posted PCIe writes that overlap the stepping of the other tiles -- and (mode 2) fetches the actions from the
+    // pinned buffer one tile ahead.  No chunk pipeline, no fill / drain: one launch and one 4-byte-per-warp copy of the
+    // done words.
+    const float* a_dev = m_act;
+    if (mode == 1) {
+      CU(cudaMemcpyAsync(h->d_act, act, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+      a_dev = (const float*)h->d_act;
+    }
+    launch_env_step32(h->dc, h->s32, a_dev, nullptr, nullptr, nullptr, nullptr, h->stream, m_out, h->d_bits, mode == 2);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(done_bits, h->d_bits, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return B747_OK;
+  }
+  // copy mode (pageable buffers, or asked for): H2D, step into device staging, D2H -- chunked like b747_step_host when
+  // the buffers are pinned
+  if (!h->d_out4) CU(cudaMalloc(&h->d_out4, sizeof(float4) * np));
+  const bool pinned = is_pinned(act) && is_pinned(out4) && is_pinned(done_bits);
+  int chunks = (pinned && n >= ((size_t)1 << 17)) ? (h->host_chunks ? h->host_chunks : 4) : 1;
+  const size_t per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+  chunks = (int)((n + per - 1) / per);
+  if (chunks > 1) {
+    if (!h->s_in) {
+      CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    }
+    while ((int)h->ev_in.size() < chunks) {
+      cudaEvent_t a, b;
+      CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      h->ev_in.push_back(a); h->ev_k.push_back(b);
+    }
+    CU(cudaEventRecord(h->ev_start, h->stream));
+    CU(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+    CU(cudaStreamWaitEvent(h->s_aux, h->ev_start, 0));
+    for (int c = 0; c < chunks; c++) {
+      const size_t lo = (size_t)c * per, hi = std::min(n, lo + per), m = hi - lo;
+      CU(cudaMemcpyAsync((float*)h->d_act + lo, act + lo, sizeof(float) * m, cudaMemcpyHostToDevice, h->s_in));
+      CU(cudaEventRecord(h->ev_in[c], h->s_in));
+      cudaStream_t sc = (c & 1) ? h->s_aux : h->stream;
+      CU(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
+      DevCfg dc = h->dc;
+      dc.env_lo = (int)lo; dc.env_hi = (int)hi;
+      launch_env_step32(dc, h->s32, (const float*)h->d_act, nullptr, nullptr, nullptr, nullptr, sc, h->d_out4, h->d_bits);
+      h->launches++;
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(h->ev_k[c], sc));
+      CU(cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+      CU(cudaMemcpyAsync(out4 + 4 * lo, h->d_out4 + lo, sizeof(float4) * m, cudaMemcpyDeviceToHost, h->s_out));
+      CU(cudaMemcpyAsync(done_bits + lo / 32, h->d_bits + lo / 32, sizeof(uint32_t) * ((m + 31) / 32), cudaMemcpyDeviceToHost, h->s_out));
+    }
+    CU(cudaEventRecord(h->ev_done, h->s_out));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_done, 0));
+    CU(cudaStreamSynchronize(h->stream));
+    return B747_OK;
+  }
+  CU(cudaMemcpyAsync(h->d_act, act, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  launch_env_step32(h->dc, h->s32, (const float*)h->d_act, nullptr, nullptr, nullptr, nullptr, h->stream, h->d_out4, h->d_bits);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out4, h->d_out4, sizeof(float4) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(done_bits, h->d_bits, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B747_OK;
+}
+
+// SB3's env.seed(s) (neural/agent.py:80): re-keys the Philox stream of every later random reset.
+extern "C" int b747_set_seed(b747_handle* h, uint64_t seed) {
+  if (!h) return fail(B747_ERR_ARG, "null handle");
+  h->cfg.seed = seed;
+  h->dc.seed = seed;
+  h->epoch++;
   return B747_OK;
 }
 

@@ -38,8 +38,11 @@ void f32_free(StateF32& s);
 bool f32_is_lean(const DevCfg& c);
 bool f32_needs_cs(const DevCfg& c);
 void f32_warm_launch();
+// out4 != nullptr: packed outputs (one float4 = obs[3] + reward per env, done flags as one bit per env in done_bits);
+// obs / rew / done / term_obs are then unused.  prefetch_actions: `actions` is host-mapped memory.
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
-                       float* term_obs, cudaStream_t s);
+                       float* term_obs, cudaStream_t s, float4* out4 = nullptr, uint32_t* done_bits = nullptr,
+                       bool prefetch_actions = false);
 void launch_reset32(const DevCfg& c, const StateF32& st, const uint8_t* mask, const b747_episode* eps, float* obs,
                     cudaStream_t s);
 void launch_defaults32(const DevCfg& c, const StateF32& st, cudaStream_t s);

@@ -262,7 +262,9 @@ __device__ __forceinline__ void load_tables32(float4* sT, const float4* __restri
 #endif
 // TIER 0: canonical family (LEAN layout); 1: general layout without the altitude loop (other observation layouts,
 // oscillating references, aero disturbance, TF reward); 2: + the altitude loop (СУ PID); 3: + recorder, tracker, signal export.
-template <int TIER, int SW = -1, bool STG = false>
+// PFA: the next tile's actions are fetched while the current tile is stepped (host-mapped action buffers: a PCIe read
+// has ~2 us of latency, a tile at K = 10 takes ~20 us).
+template <int TIER, int SW = -1, bool STG = false, bool PFA = false>
 #ifdef B747_F32_MAXNREG
 #define B747_STEP_BOUNDS __launch_bounds__(TIER == 0 ? B747_F32_THREADS : 128) __maxnreg__(TIER == 0 ? B747_F32_MAXNREG : 168)
 #else
@@ -270,7 +272,8 @@ template <int TIER, int SW = -1, bool STG = false>
 #endif
 __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
-                                                    uint8_t* __restrict__ done_out, float* __restrict__ term_obs) {
+                                                    uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
+                                                    float4* __restrict__ out4, uint32_t* __restrict__ done_bits) {
   // Persistent warps: the launch fills the GPU once (blocks = SMs x resident blocks per SM), the tables are staged into
   // shared memory once per block, and every warp then walks its own stride of 32-env tiles with no block-level
   // synchronisation until the episode statistics are flushed at the very end.
@@ -295,7 +298,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
   load_tables32(sT, st.tables);
   uint32_t phase = 0;
   float a_next = 0.f;
-  if (STAGED && wt0 < n_tiles && c.env_lo + wt0 * 32 + lane < c.env_hi) a_next = actions[c.env_lo + wt0 * 32 + lane];
+  if ((STAGED || PFA) && wt0 < n_tiles && c.env_lo + wt0 * 32 + lane < c.env_hi) a_next = actions[c.env_lo + wt0 * 32 + lane];
 #pragma unroll 1
   for (int wt = wt0; wt < n_tiles; wt += wstride) {
   const int i = c.env_lo + wt * 32 + lane;
@@ -315,10 +318,14 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
       if (c.env_lo + wn * 32 + lane < c.env_hi) a_next = actions[c.env_lo + wn * 32 + lane];
     }
   }
+  if (PFA && !STAGED) {
+    const int in = i + wstride * 32;
+    if (in < c.env_hi) a_next = actions[in];
+  }
   if (live) {
     if (!STAGED) {
       load_mx<GEN, CS>(st, np, i, r);
-      a = actions[i];
+      if (!PFA) a = actions[i];
     }
     if (c.norm_act) a *= (float)c.action_max;
     const bool use_ctrl = CS && (r.flags & FL_USE_CTRL);
@@ -457,10 +464,18 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
       SG(V, o.V); SG(Mach, o.Mach);
 #undef SG
     }
-    rew_out[i] = rew;
-    done_out[i] = done ? 1 : 0;
-    if (term_obs)
-      for (int k = 0; k < od; k++) term_obs[(size_t)i * od + k] = obs[k];
+    // Outputs.  Packed form (b747_step*_packed, observation layouts of three scalars): ONE 128-bit store per env --
+    // (obs before any auto-reset, reward) -- and the done flags as one ballot word per warp (below); the observation after
+    // an auto-reset is all zeros (ControllerEnv.reset), so the caller derives it from the done bit.
+    const bool packed = out4 != nullptr;
+    if (packed) {
+      out4[i] = make_float4(obs[0], obs[1], obs[2], rew);
+    } else {
+      rew_out[i] = rew;
+      done_out[i] = done ? 1 : 0;
+      if (term_obs)
+        for (int k = 0; k < od; k++) term_obs[(size_t)i * od + k] = obs[k];
+    }
     bool full_store = false;
     if (done) {
       ep_ret = r.ep_return; ep_len = (double)(r.tick / c.substeps);
@@ -477,13 +492,19 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
         if (TRACE && st.sig) for (int k = 0; k < NSIG; k++) st.sig[(size_t)k * np + i] = 0.f;
       }
     }
-    if (od == 3) {  // canonical layout: three contiguous floats per env
-      float* q = obs_out + (size_t)i * 3;
-      q[0] = obs[0]; q[1] = obs[1]; q[2] = obs[2];
-    } else {
-      for (int k = 0; k < od; k++) obs_out[(size_t)i * od + k] = obs[k];
+    if (!packed) {
+      if (od == 3) {  // canonical layout: three contiguous floats per env
+        float* q = obs_out + (size_t)i * 3;
+        q[0] = obs[0]; q[1] = obs[1]; q[2] = obs[2];
+      } else {
+        for (int k = 0; k < od; k++) obs_out[(size_t)i * od + k] = obs[k];
+      }
     }
     store_mx<GEN, CS>(st, np, i, r, full_store);
+  }
+  if (done_bits) {  // done flags of the tile as one word (env_lo is a multiple of 32: launch_env_step32)
+    const unsigned b = __ballot_sync(0xffffffffu, done);
+    if (lane == 0) done_bits[(c.env_lo >> 5) + wt] = b;
   }
   warp_episode_stats(s_stats, done, ep_ret, ep_len);
   }
@@ -566,17 +587,21 @@ static MP32 make_mp32(const ModelParams& m) {
 
 int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t stream) {
   const size_t np = (size_t)c.n_pad;
-  if (cudaMalloc(&s.D, sizeof(double2) * np * ND_GROUPS) != cudaSuccess) return -1;
-  if (cudaMalloc(&s.F, sizeof(float4) * np * NF_GROUPS) != cudaSuccess) return -1;
-  if (export_signals && cudaMalloc(&s.sig, sizeof(float) * np * NSIG) != cudaSuccess) return -1;
-  if (cudaMalloc(&s.stats, sizeof(double) * 4) != cudaSuccess) return -1;
-  if (cudaMalloc(&s.last_ret, sizeof(double) * np) != cudaSuccess) return -1;
-  if (cudaMalloc(&s.last_len, sizeof(int) * np) != cudaSuccess) return -1;
-  {
-    const ft::Fast F = ft::build();
-    if (!F.ok) return -2;  // model_simple_P does not fit the compiled table layout
-    if (cudaMalloc(&s.tables, sizeof(float4) * ft::CELLS) != cudaSuccess) return -1;
-    if (cudaMemcpy(s.tables, F.v.data(), sizeof(float4) * ft::CELLS, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  const ft::Fast F = ft::build();
+  if (!F.ok) return -2;  // model_simple_P does not fit the compiled table layout (checked before anything is allocated)
+  bool ok = cudaMalloc(&s.D, sizeof(double2) * np * ND_GROUPS) == cudaSuccess &&
+            cudaMalloc(&s.F, sizeof(float4) * np * NF_GROUPS) == cudaSuccess &&
+            (!export_signals || cudaMalloc(&s.sig, sizeof(float) * np * NSIG) == cudaSuccess) &&
+            cudaMalloc(&s.stats, sizeof(double) * 4) == cudaSuccess &&
+            cudaMalloc(&s.last_ret, sizeof(double) * np) == cudaSuccess &&
+            cudaMalloc(&s.last_len, sizeof(int) * np) == cudaSuccess &&
+            cudaMalloc(&s.tables, sizeof(float4) * ft::CELLS) == cudaSuccess &&
+            cudaMemcpy(s.tables, F.v.data(), sizeof(float4) * ft::CELLS, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) {  // release whatever was allocated: a retry with fewer envs must find the HBM free
+    const cudaError_t e = cudaGetLastError();
+    f32_free(s);
+    (void)e;
+    return -1;
   }
   cudaMemsetAsync(s.D, 0, sizeof(double2) * np * ND_GROUPS, stream);
   cudaMemsetAsync(s.F, 0, sizeof(float4) * np * NF_GROUPS, stream);
@@ -594,8 +619,9 @@ static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 #ifndef B747_PERSISTENT
 #define B747_PERSISTENT 1  // 0: one 128-env tile per block (grid = all tiles)
 #endif
-// grid of the step kernel: enough blocks to fill every SM at the kernel's occupancy, never more than the tiles need
-template <int TIER>
+// grid of the step kernel: enough blocks to fill every SM at the occupancy of the instantiation that is launched,
+// never more than the tiles need
+template <int TIER, int SW = -1, bool STG = false, bool PFA = false>
 static int step_grid(int n) {
   constexpr int threads = TIER == 0 ? B747_F32_THREADS : 128;
   const int need = grid_for(n, threads);
@@ -607,35 +633,45 @@ static int step_grid(int n) {
   if (!resident[dev]) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step32<TIER>, threads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step32<TIER, SW, STG, PFA>, threads, 0);
     resident[dev] = sms > 0 && per_sm > 0 ? sms * per_sm : need;
   }
   return need < resident[dev] ? need : resident[dev];
 }
 
 // resolve the persistent grids once, outside any stream capture (b747_create)
-void f32_warm_launch() { step_grid<0>(1 << 30); step_grid<1>(1 << 30); step_grid<2>(1 << 30); step_grid<3>(1 << 30); }  // occupancy is per tier (same launch bounds for every SW)
+void f32_warm_launch() {
+  const int big = 1 << 30;
+  step_grid<0, SW_RP, false, true>(big); step_grid<0, SW_RP, true>(big); step_grid<0, SW_RP>(big); step_grid<0>(big);
+  step_grid<1, SW_RP>(big); step_grid<1>(big); step_grid<2>(big); step_grid<3>(big);
+}
 
 void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions, float* obs, float* rew, uint8_t* done,
-                       float* term_obs, cudaStream_t s) {
+                       float* term_obs, cudaStream_t s, float4* out4, uint32_t* done_bits, bool prefetch_actions) {
   const MP32 mp = make_mp32(c.mp);
   const int n = c.env_hi - c.env_lo;
   if (n <= 0) return;
   const bool plain = !st.trace.trk && !st.trace.rec && !st.sig && !c.force_full;
-  if (plain && f32_is_lean(c) && mp.sw == SW_RP && c.substeps <= B747_STAGED_MAX_K)  // HBM-bound regime: TMA-staged state
-    k_env_step32<0, SW_RP, true><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+#define B747_LAUNCH(TIER, ...) \
+  k_env_step32<TIER, ##__VA_ARGS__><<<step_grid<TIER, ##__VA_ARGS__>(n), TIER == 0 ? B747_F32_THREADS : 128, 0, s>>>( \
+      c, mp, st, actions, obs, rew, done, term_obs, out4, done_bits)
+  if (plain && f32_is_lean(c) && mp.sw == SW_RP && prefetch_actions)  // host-mapped action buffer (b747_step_host_packed)
+    B747_LAUNCH(0, SW_RP, false, true);
+  else if (plain && f32_is_lean(c) && mp.sw == SW_RP && c.substeps <= B747_STAGED_MAX_K)  // HBM-bound regime: TMA-staged state
+    B747_LAUNCH(0, SW_RP, true);
   else if (plain && f32_is_lean(c) && mp.sw == SW_RP)  // the canonical switch setting (use_RP only) as a compile-time constant
-    k_env_step32<0, SW_RP><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    B747_LAUNCH(0, SW_RP);
   else if (plain && f32_is_lean(c))
-    k_env_step32<0><<<step_grid<0>(n), B747_F32_THREADS, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    B747_LAUNCH(0);
   else if (plain && !f32_needs_cs(c) && mp.sw == SW_RP)
-    k_env_step32<1, SW_RP><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    B747_LAUNCH(1, SW_RP);
   else if (plain && !f32_needs_cs(c))
-    k_env_step32<1><<<step_grid<1>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    B747_LAUNCH(1);
   else if (plain)
-    k_env_step32<2><<<step_grid<2>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    B747_LAUNCH(2);
   else
-    k_env_step32<3><<<step_grid<3>(n), 128, 0, s>>>(c, mp, st, actions, obs, rew, done, term_obs);
+    B747_LAUNCH(3);
+#undef B747_LAUNCH
 }
 void launch_reset32(const DevCfg& c, const StateF32& st, const uint8_t* mask, const b747_episode* eps, float* obs,
                     cudaStream_t s) {

@@ -142,9 +142,10 @@ class BatchEngine:
     def reset(self, obs=None, mask=None):
         check(self._L.b747_reset(self._h, _ptr(mask), _ptr(obs)))
 
-    def reset_to(self, episodes, obs=None):
+    def reset_to(self, episodes, obs=None, mask=None):
+        """Explicit episodes (Controller.reset(state0)); mask: device uint8 tensor selecting the envs to reset."""
         arr = (Episode * self.n_envs)(*episodes)
-        check(self._L.b747_reset_to(self._h, arr, _ptr(obs)))
+        check(self._L.b747_reset_to_masked(self._h, arr, _ptr(mask), _ptr(obs)))
 
     def step(self, actions, obs, rew, done, terminal_obs=None):
         """Device pointers in, asynchronous on the handle's stream."""
@@ -160,6 +161,25 @@ class BatchEngine:
         if terminal_obs is not None:
             return obs, rew, done, terminal_obs
         return obs, rew, done
+
+    def step_packed(self, actions, out4, done_bits):
+        """Device tensors: out4 [n_envs, 4] float32 = (obs before auto-reset, reward), done_bits [(n_envs+31)//32]
+        int32/uint32 (one bit per env).  f32 handles with a 3-scalar observation layout.  Asynchronous."""
+        check(self._L.b747_step_packed(self._h, _ptr(actions), _ptr(out4), _ptr(done_bits)))
+
+    def step_host_packed(self, actions, out4, done_bits):
+        """Host buffers (float32 [n_envs], float32 [n_envs, 4], uint32 [(n_envs+31)//32]); page-locked buffers are read
+        and written by the kernel directly (zero-copy).  Synchronised on return."""
+        check(self._L.b747_step_host_packed(self._h, _ptr(actions), _ptr(out4), _ptr(done_bits)))
+
+    def set_host_mode(self, mode):
+        """step_host_packed with pinned buffers: -1 automatic, 0 staged copies, 1 zero-copy records, 2 zero-copy both."""
+        check(self._L.b747_set_host_mode(self._h, int(mode)))
+
+    def set_seed(self, seed):
+        """env.seed(s): re-key the Philox stream of every later random reset."""
+        check(self._L.b747_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
+        self.cfg.seed = int(seed) & (2 ** 64 - 1)
 
     def set_host_chunks(self, n_chunks):
         """Chunks of step_host's copy/compute pipeline: 0 = automatic, 1 = one launch."""

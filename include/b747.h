@@ -106,6 +106,9 @@ int b747_reset(b747_handle *h, const uint8_t *mask_dev, void *obs_dev);
 /* Deterministic reset: episodes is a HOST array of n_envs descriptors (Controller.reset(state0) with
  * an explicit reference, as neural/callbacks.py:61-100 does). */
 int b747_reset_to(b747_handle *h, const b747_episode *episodes_host, void *obs_dev);
+/* Same, for the envs with mask_dev[i] != 0 only (mask on the device like b747_reset's; NULL = all): what
+ * `vec_env.env_method("reset", state0, indices=[i])` of the SB3 contract needs.  obs rows of other envs are untouched. */
+int b747_reset_to_masked(b747_handle *h, const b747_episode *episodes_host, const uint8_t *mask_dev, void *obs_dev);
 
 /* ControllerEnv.step for all envs: device buffers of the handle dtype.
  *   actions [n_envs]; obs [n_envs][obs_dim]; rew [n_envs]; done [n_envs] (uint8);
@@ -120,6 +123,24 @@ int b747_step(b747_handle *h, const void *actions_dev, void *obs_dev, void *rew_
 int b747_step_host(b747_handle *h, const void *actions, void *obs, void *rew, uint8_t *done, void *terminal_obs);
 /* Number of chunks of b747_step_host's pipeline: 0 = automatic (4 from 128 Ki envs, else 1), 1 = no pipeline. */
 int b747_set_host_chunks(b747_handle *h, int n_chunks);
+
+/* Packed outputs (f32 handles, observation layouts of three scalars = ObservationType.PID_LIKE): per env ONE record
+ *   out4[i] = { obs[0], obs[1], obs[2], reward }   -- the observation BEFORE any auto-reset, i.e. SB3's
+ *                                                    infos[i]["terminal_observation"] where the env finished;
+ *   bit (i & 31) of done_bits[i >> 5] = done flag  -- done_bits holds (n_envs + 31) / 32 words.
+ * The observation after an auto-reset is all zeros (every exported signal is zero after Model.initialize,
+ * env/ctrl_env.py:273-278), so a caller derives the returned observation as done ? 0 : out4[i].obs.
+ * b747_step_packed: device buffers, asynchronous on the handle's stream.
+ * b747_step_host_packed: HOST buffers, synchronised on return.  With page-locked (cudaHostAlloc / cudaHostRegister)
+ * buffers the kernel reads the actions from and stores the records into the caller's memory directly (posted PCIe
+ * writes of 512 contiguous bytes per warp that overlap the stepping of the other envs); pageable buffers are staged. */
+int b747_step_packed(b747_handle *h, const float *actions_dev, float *out4_dev, uint32_t *done_bits_dev);
+int b747_step_host_packed(b747_handle *h, const float *actions, float *out4, uint32_t *done_bits);
+/* Host path of b747_step_host_packed with page-locked buffers: -1 automatic (2), 0 staged copies (chunk pipeline),
+ * 1 actions copied / records stored zero-copy, 2 actions and records zero-copy. */
+int b747_set_host_mode(b747_handle *h, int mode);
+/* env.seed(s) of the gym / SB3 API (neural/agent.py:80): re-keys the Philox stream used by every later random reset. */
+int b747_set_seed(b747_handle *h, uint64_t seed);
 
 /* Raw model stepping (Model.step xN, core/model.py:247-250): no action law, no reward (f64 handles).
  * b747_model_initialize == Model.initialize (core/model.py:238-244): re-reads state0_*, zeroes time,

@@ -91,3 +91,16 @@ void b747o_batch_step(b747o_batch *b, const double *actions, double *obs, double
 
 b747o_env *b747o_batch_env(b747o_batch *b, int64_t i) { return &b->envs[i]; }
 b747o_model *b747o_batch_model(b747o_batch *b, int64_t i) { return &b->models[i]; }
+
+/* named field `name`[idx] of every model of the batch (per-step state / signal parity checks) */
+double *b747o_model_ptr(b747o_model *m, const char *n);
+int b747o_batch_gather(b747o_batch *b, const char *name, int idx, double *out) {
+  const double *p0 = b747o_model_ptr(&b->models[0], name);
+  if (!p0) return -1;
+  const size_t off = (size_t)((const char *)(p0 + idx) - (const char *)&b->models[0]);
+  for (int64_t i = 0; i < b->n; i++) out[i] = *(const double *)((const char *)&b->models[i] + off);
+  return 0;
+}
+void b747o_batch_ticks(b747o_batch *b, int64_t *out) {
+  for (int64_t i = 0; i < b->n; i++) out[i] = (int64_t)b->models[i].tick;
+}

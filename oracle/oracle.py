@@ -229,6 +229,8 @@ def olib():
         L.b747o_batch_model.restype = ctypes.c_void_p
         L.b747o_batch_model.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         L.b747o_philox4x32.argtypes = [ctypes.POINTER(ctypes.c_uint32)] * 3
+        L.b747o_batch_gather.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p]
+        L.b747o_batch_ticks.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         _olib = L
     return _olib
 
@@ -323,6 +325,18 @@ class OracleBatch:
 
     def model(self, i):
         return CModel(self._L.b747o_batch_model(self._h, i))
+
+    def gather(self, name, idx=0):
+        """Field `name`[idx] of every env's model (the DLL-global view), as one float64 array."""
+        out = np.empty(self.n)
+        if self._L.b747o_batch_gather(self._h, name.encode(), int(idx), _dptr(out)):
+            raise KeyError(name)
+        return out
+
+    def ticks(self):
+        out = np.empty(self.n, np.int64)
+        self._L.b747o_batch_ticks(self._h, _dptr(out))
+        return out
 
     def env(self, i):
         """Recorder view of env i (enable_storage / storage / stepinfo_SS / stepinfo_CS)."""

@@ -157,10 +157,205 @@ def test_vec_env_contract(oracle):
                 assert infos[i]["episode"]["l"] == 10 and infos[i]["episode"]["r"] > 0
         else:
             assert not dones.any() and infos[0] == {}
-    assert venv.env_is_wrapped(None) == [False] * n and venv.seed(1) == [1] * n
+    assert venv.env_is_wrapped(None) == [False] * n and venv.seed(1) == [1 + i for i in range(n)]
     st = venv.episode_stats()
     assert st[0] == 2 * n and st[2] == 20 * n
     venv.close()
+
+
+@pytest.mark.parametrize("n,mode", [(1000, -1), (1000, 0), (1000, 1), (200000, -1), (200000, 0), (777, "pageable")])
+def test_packed_host_step_equals_plain_step(n, mode):
+    """b747_step_host_packed (one float4 record per env + done bits; zero-copy on pinned buffers, staged copies
+    otherwise) returns exactly what b747_step_host returns: record = (terminal observation, reward), bit = done."""
+    import torch
+    from b747_rl_ctrl_b200 import engine as E
+    kw = dict(dtype=E.F32, seed=6, sample_time=0.05, tk=0.35)  # 7-step episodes: auto-resets inside the run
+    ref, pk = E.BatchEngine(n_envs=n, **kw), E.BatchEngine(n_envs=n, **kw)
+    ref.reset(); pk.reset()
+    nw = (n + 31) // 32
+    if mode == "pageable":
+        act, out4, bits = np.zeros(n, np.float32), np.zeros((n, 4), np.float32), np.zeros(nw, np.uint32)
+    else:
+        pk.set_host_mode(mode)
+        keep = [torch.zeros(n).pin_memory(), torch.zeros(n, 4).pin_memory(), torch.zeros(nw, dtype=torch.int32).pin_memory()]
+        act, out4, bits = keep[0].numpy(), keep[1].numpy(), keep[2].numpy().view(np.uint32)
+    rng = np.random.default_rng(2)
+    term = np.zeros((n, 3), np.float32)
+    n_done = 0
+    for k in range(16):
+        a = rng.uniform(-1, 1, n).astype(np.float32)
+        _, rew, done, term = ref.step_host(a, terminal_obs=term)
+        act[:] = a
+        out4[:] = -7.0
+        bits[:] = 0xdeadbeef
+        pk.step_host_packed(act, out4, bits)
+        d = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n]
+        assert np.array_equal(d, done), k
+        assert np.array_equal(out4[:, :3], term) and np.array_equal(out4[:, 3], rew), k
+        n_done += int(done.sum())
+    assert n_done == 2 * n
+    s0, s1 = ref.episode_stats(), pk.episode_stats()
+    assert s0[0] == s1[0] == 2 * n and np.allclose(s0, s1, rtol=1e-12)
+    for name in ("h", "th", "tick", "ep_idx", "ep_return"):
+        assert np.array_equal(ref.get(name), pk.get(name)), name
+    # device-buffer form
+    act_d, out_d = torch.zeros(n, device="cuda"), torch.zeros(n, 4, device="cuda")
+    bits_d = torch.zeros(nw, dtype=torch.int32, device="cuda")
+    a = rng.uniform(-1, 1, n).astype(np.float32)
+    _, rew, done, term = ref.step_host(a, terminal_obs=term)
+    act_d.copy_(torch.from_numpy(a))
+    pk.step_packed(act_d, out_d, bits_d)
+    pk.synchronize()
+    assert np.array_equal(out_d.cpu().numpy()[:, 3], rew) and np.array_equal(out_d.cpu().numpy()[:, :3], term)
+    ref.close(); pk.close()
+
+
+def test_packed_step_rejected_where_it_does_not_apply():
+    from b747_rl_ctrl_b200 import engine as E
+    e = E.BatchEngine(n_envs=64, dtype=E.F32, obs_type=E.OBS_SPEED_MODE)
+    with pytest.raises(E.B747Error):
+        e.step_host_packed(np.zeros(64, np.float32), np.zeros((64, 4), np.float32), np.zeros(2, np.uint32))
+    e.close()
+    e = E.BatchEngine(n_envs=64, dtype=E.F64)
+    with pytest.raises(E.B747Error):
+        e.step_host_packed(np.zeros(64, np.float32), np.zeros((64, 4), np.float32), np.zeros(2, np.uint32))
+    e.close()
+
+
+@pytest.mark.parametrize("copy_outputs", [True, False])
+def test_vec_env_under_sb3_standin(oracle, copy_outputs):
+    """The numpy-mode VecEnv (packed zero-copy path) driven the way stable-baselines3 drives it: float32 [N, 1] actions
+    through step_async / step_wait inside a VecMonitor, in collect_rollouts' call order (an observation is read once
+    more after the NEXT step returned).  Checked against the oracle: observations (zero where an env finished),
+    rewards, dones, terminal observations, and the episode records of both the env's own monitor and VecMonitor."""
+    import sb3_standin as sb3
+    from b747_rl_ctrl_b200.vec_env import B747VecEnv
+    n = 300
+    venv = B747VecEnv(n, tk=0.5, sample_time=0.05, seed=4, copy_outputs=copy_outputs)  # f32, 10-step episodes
+    assert sb3.conforms(venv) == []
+    env = sb3.VecMonitor(venv)
+    assert env.seed(4) == [4 + i for i in range(n)]
+    obs = env.reset()
+    assert obs.shape == (n, 3) and obs.dtype == np.float32 and (obs == 0).all()
+    ob = oracle.OracleBatch(oracle.make_cfg(tk=0.5, seed=4), n)
+    ob.reset()
+    rng = np.random.default_rng(1)
+    roll = sb3.collect_rollouts(env, lambda o: rng.uniform(-1.2, 1.2, (n, 1)), 25, obs)   # some actions get clipped
+    assert roll["obs"].shape == (25, n, 3) and roll["done"].dtype == bool
+    rets = np.zeros(n)
+    k_term = 0
+    for k in range(25):
+        a = np.clip(roll["act"][k][:, 0], -1, 1).astype(np.float64)
+        o_o, r_o, d_o, t_o = ob.step(a)
+        rets += r_o
+        assert np.array_equal(roll["done"][k], d_o)
+        assert np.abs(roll["rew"][k] - r_o).max() <= 1e-3
+        nxt = roll["obs"][k + 1] if k + 1 < 25 else roll["last_obs"]
+        assert np.abs(nxt - o_o).max() <= 1e-5, k              # what collect_rollouts stored one step later
+        if d_o.any():
+            assert d_o.all() and (nxt == 0).all()
+            for i in range(n):
+                j, tobs, epi = roll["terminal"][k_term]
+                k_term += 1
+                assert j == i and np.abs(tobs - t_o[i]).max() <= 1e-5
+                assert epi["l"] == 10 and abs(epi["r"] - rets[i]) <= 1e-2
+            rets[:] = 0
+    assert k_term == 2 * n
+    venv.close()
+
+
+def test_vec_env_per_env_views(oracle):
+    """get_attr / set_attr / env_method address single environments (what SubprocVecEnv forwards to its workers):
+    `env.get_attr('ctrl')[0].storage.storage` (neural/setups.py:216), `env.ctrl.vartheta_func = lambda _: ref`,
+    `ctrl.quality()`, `envs[i].reset(state0)`; seed(s) re-keys the Philox stream of later resets."""
+    from b747_rl_ctrl_b200.vec_env import B747VecEnv
+    from b747_rl_ctrl_b200 import engine as E
+    n = 8
+    venv = B747VecEnv(n, tk=2.0, sample_time=0.05, seed=3, dtype=E.F64, record_capacity=260, export_signals=True)
+    venv.reset()
+    ctrls = venv.get_attr("ctrl")
+    assert len(ctrls) == n and ctrls[0] is venv.ctrl and ctrls[3] is venv.envs[3].ctrl
+    assert venv.get_attr("ctrl", indices=[2, 5])[1] is ctrls[5]
+    assert venv.get_attr("norm_obs") == [True] * n and venv.get_attr("tk", indices=1) == [2.0]
+    # re-target env 2 and restart env 5 from an explicit state, leave the others alone
+    ctrls[2].vartheta_func = lambda _: 4 * DEG
+    h_before = venv.engine.get("h")
+    ctrls[5].vartheta_func = lambda _: -3 * DEG
+    venv.env_method("reset", np.array([0, 9000, 240, 0, 0, 0]), indices=[5])
+    h_after = venv.engine.get("h")
+    assert h_after[5] == 9000.0 and np.array_equal(np.delete(h_after, 5), np.delete(h_before, 5))
+    assert ctrls[2].vartheta_ref == 4 * DEG and ctrls[5].vartheta_ref == -3 * DEG
+    rng = np.random.default_rng(0)
+    for k in range(7):
+        obs, rew, dones, infos = venv.step(rng.uniform(-1, 1, (n, 1)))
+    st = ctrls[5].storage.storage                       # Controller.storage: one record per MODEL step
+    assert len(st["t"]) == 35 and st["t"][-1] == pytest.approx(0.35) and st["y"][0] == pytest.approx(9000.0, abs=5)
+    assert set(st) >= {"t", "U_com", "U_PID", "deltaz", "hzh", "vartheta_ref", "U_RL", "x", "y", "Vx", "Vy", "vartheta", "wz"}
+    assert st["vartheta_ref"][-1] == pytest.approx(-3.0)
+    q = ctrls[2].quality()
+    assert 0 < q <= 1 and q == pytest.approx(math.exp(-6 * ctrls[2].model.ITSE / (2.0 * (4 * DEG) ** 2)))
+    assert venv.env_method("get_reward", indices=[1]) == [pytest.approx(float(rew[1]))]
+    assert np.allclose(venv.get_attr("state_box", indices=[4])[0], obs[4])
+    assert ctrls[0].model.time == pytest.approx(0.35) and not ctrls[0].is_done
+    with pytest.raises(NotImplementedError):
+        ctrls[1].vartheta_func = lambda t: 0.01 * t   # the batched kernels hold a reference constant over an episode
+    # seed(s): later random resets draw from the re-keyed stream, identically to a handle built with that seed
+    venv.seed(11)
+    venv.env_method("reset", indices=[0, 1])
+    other = E.BatchEngine(n_envs=n, dtype=E.F64, seed=11, tk=2.0)
+    other.set("ep_idx", venv.engine.get("ep_idx") - np.array([1, 1] + [0] * (n - 2)))
+    other.reset()
+    assert np.array_equal(other.get("h")[:2], venv.engine.get("h")[:2])
+    assert not np.array_equal(venv.engine.get("h")[:2], h_before[:2])
+    other.close()
+    venv.close()
+
+
+def test_controller_time_varying_reference_function():
+    """Controller(vartheta_func=<any callable>): the reference is func(model.time) written before every env step
+    (core/controller.py:233-236).  A 3-sine Python function must reproduce the in-kernel oscillating reference."""
+    from b747_rl_ctrl_b200.core.controller import Controller, CtrlMode, CtrlType
+    from b747_rl_ctrl_b200 import engine as E
+    A, f = [3 * DEG, 2 * DEG, 1 * DEG], [0.05, 0.2, 0.4]
+    func = lambda t: sum(a * math.sin(2 * math.pi * w * t) for a, w in zip(A, f))
+    c = Controller(CtrlType.MANUAL, CtrlMode.DIRECT_CONTROL, tk=3.0, sample_time=0.05, vartheta_func=func)
+    c.reset(np.array([0, 9000, 230, 2, 0, 0]))
+    ref = E.BatchEngine(n_envs=1, dtype=E.F64, reset_ref_mode=E.RESET_NONE, tk=3.0, sample_time=0.05, norm_act=False,
+                        auto_reset=False)
+    ref.reset_to([E.episode([0, 9000, 230, 2, 0, 0], osc=(A, f))])
+    rng = np.random.default_rng(5)
+    for k in range(60):
+        a = rng.uniform(-0.2, 0.2, 1)
+        c.step(a)
+        o_r, r_r, d_r = ref.step_host(a)
+        obs, rew, done = c._last
+        assert np.abs(obs - o_r[0]).max() <= 1e-11 and abs(rew - r_r[0]) <= 1e-10 and done == bool(d_r[0]), k
+        assert c.vartheta_ref == pytest.approx(func(k * 0.05), abs=1e-15)
+    assert done and abs(obs[1]) > 1e-4
+    # altitude reference through the СУ PID: h_func(t) is written to h_zh when the altitude loop is closed
+    c2 = Controller(CtrlType.SEMI_MANUAL, CtrlMode.ADD_PROC_CONTROL, tk=2.0, sample_time=0.05, action_max=1.0,
+                    h_func=lambda t: 11000.0 + 20.0 * t)
+    c2.reset(np.array([0, 11000, 250, 0, 0, 0]))
+    for k in range(10):
+        c2.step(np.array([0.0]))
+    assert c2.model.hzh == pytest.approx(11000.0 + 20.0 * 0.45)
+    ref.close()
+
+
+def test_controller_draws_aero_disturbance_on_every_reset():
+    """core/controller.py:181-191: DisturbanceMode.AERO_DISTURBANCE without a fixed aero_err draws a fresh Gaussian error
+    from numpy's global stream on every reset, also when the reset itself is deterministic (reset_ref_mode None)."""
+    from b747_rl_ctrl_b200.core.controller import Controller, CtrlMode, CtrlType, DisturbanceMode
+    c = Controller(CtrlType.MANUAL, CtrlMode.DIRECT_CONTROL, disturbance_mode=DisturbanceMode.AERO_DISTURBANCE, tk=1.0,
+                   vartheta_func=lambda _: 0.05)
+    np.random.seed(0)
+    want = [np.array([np.random.normal(m, 0.5) for m in (-0.1, 0.1, -0.1, -0.1, 0.1)]) for _ in range(2)]
+    np.random.seed(0)
+    for k in range(2):
+        c.reset(np.array([0, 11000, 250, 0, 0, 0]))
+        assert np.allclose(c.model.aero_err, want[k], rtol=0, atol=0)
+    c.step(np.array([0.01]))
+    assert c.model.CYa != 0.0
 
 
 def test_vec_env_device_tensors():

@@ -25,14 +25,54 @@ def E():
     return engine
 
 
-def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=None, sticky=0, strict=True):
+
+# ---- per-step state / signal parity (float64 handles with export_signals) -------------------------------------------
+# b747 field name -> (oracle name, index, floor).  The bar is |d| <= 1e-9 * (|ref| + floor): 1e-9 relative (north_star)
+# with an absolute floor at the field's resolution of interest, so that zero crossings do not make the bar vacuous.
+X_FIELDS = {
+    "x": ("X", 0, 1.0), "h": ("X", 1, 1.0), "q0": ("X", 2, 1.0), "q3": ("X", 5, 1e-2), "Vx": ("X", 6, 1.0),
+    "Vy": ("X", 7, 1.0), "wz": ("X", 8, 1e-3), "cs_int": ("X", 9, 1e-3), "cs_flt": ("X", 10, 1e-3),
+    "ss_int": ("X", 11, 1e-3), "ss_flt": ("X", 12, 1e-3), "dv_int": ("X", 13, 1e-3), "itae": ("X", 14, 1e-3),
+    "iae": ("X", 15, 1e-3), "ise": ("X", 16, 1e-4), "itse": ("X", 17, 1e-4),
+}
+SIG_FIELDS = {
+    "sig_state_x": ("state", 0, 1.0), "sig_state_y": ("state", 1, 1.0), "sig_state_Vx": ("state", 2, 1.0),
+    "sig_state_Vy": ("state", 3, 1.0), "sig_state_vartheta": ("state", 4, 1e-3), "sig_state_wz": ("state", 5, 1e-3),
+    "sig_sim_time": ("sim_time", 0, 0.0), "sig_vartheta_zh": ("vartheta_zh", 0, 1e-3),
+    "sig_U_com_PID": ("U_com_PID", 0, 1e-3), "sig_CXa": ("CXa", 0, 1e-3), "sig_CYa": ("CYa", 0, 1e-2),
+    "sig_mz": ("mz", 0, 1e-3), "sig_K_alpha": ("K_alpha", 0, 1e-2), "sig_dCm_ddeltaz": ("dCm_ddeltaz", 0, 1e-4),
+    "sig_U_com": ("U_com", 0, 1e-3), "sig_deltaz_RP": ("deltaz_RP", 0, 1e-3), "sig_dvartheta": ("dvartheta", 0, 1e-3),
+    "sig_dvartheta_int": ("dvartheta_int", 0, 1e-3), "sig_dvartheta_dt": ("dvartheta_dt", 0, 1e-3),
+    "sig_TAE": ("TAE", 0, 1e-3), "sig_ITAE": ("ITAE", 0, 1e-3), "sig_TSE": ("TSE", 0, 1e-4),
+    "sig_ITSE": ("ITSE", 0, 1e-4), "sig_AE": ("AE", 0, 1e-3), "sig_IAE": ("IAE", 0, 1e-3), "sig_SE": ("SE", 0, 1e-4),
+    "sig_ISE": ("ISE", 0, 1e-4), "sig_alpha": ("alpha", 0, 1e-3), "sig_V": ("V", 0, 1.0), "sig_Mach": ("Mach", 0, 1e-2),
+}
+# the second finite difference over 10 ms amplifies 1-ulp libm differences by 1/h^2 (SURVEY.md 7 hard part 3)
+DDT2 = ("sig_dvartheta_dt_dt", "dvartheta_dt_dt", 1e-9, 1e-6)
+
+
+def _field_ratios(eng, ob, ratios):
+    """max over envs of |engine field - oracle field| / bar, accumulated per field into `ratios`."""
+    for name, (oname, idx, floor) in {**X_FIELDS, **SIG_FIELDS}.items():
+        ref = ob.gather(oname, idx)
+        bar = 1e-9 * (np.abs(ref) + floor)
+        bar[bar == 0] = 1e-300   # sim_time: exact
+        ratios[name] = max(ratios.get(name, 0.0), float((np.abs(eng.get(name) - ref) / bar).max()))
+    name, oname, a, r = DDT2
+    ref = ob.gather(oname)
+    ratios[name] = max(ratios.get(name, 0.0), float((np.abs(eng.get(name) - ref) / (a + r * np.abs(ref))).max()))
+    assert np.array_equal(eng.get("tick").astype(np.int64), ob.ticks()), "model tick counters differ"
+
+
+def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=None, sticky=0, strict=True, fields=False):
     """Step engine and oracle in lock-step with the same actions; returns the worst deviations.
     strict=False: done flags are still compared bit for bit, but observation / reward deviations are only recorded per
     environment as multiples of the tolerance (eng.env_ratio) -- for configuration families whose unstable members
     amplify any rounding difference without bound, where the statement is about quantiles over environments."""
     cfg_o = O.make_cfg(seed=seed, **kw)
-    eng = E.BatchEngine(n_envs=n, dtype=dtype, seed=seed, auto_reset=True, **kw)
+    eng = E.BatchEngine(n_envs=n, dtype=dtype, seed=seed, auto_reset=True, export_signals=fields, **kw)
     ob = O.OracleBatch(cfg_o, n)
+    ratios = {}
     eng.reset()
     o0 = ob.reset()
     assert (o0 == 0).all()
@@ -65,6 +105,12 @@ def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=N
         env_ratio = np.maximum(env_ratio, np.maximum((et / lim).max(axis=1), er / rew_tol))
         worst_o, worst_r = max(worst_o, et.max()), max(worst_r, er.max())
         env_worst = np.maximum(env_worst, et.max(axis=1))
+        if fields:
+            _field_ratios(eng, ob, ratios)
+    if fields:
+        bad = {k: v for k, v in ratios.items() if not v <= 1.0}
+        print("state/signal deviation / bar, worst fields:", sorted(ratios.items(), key=lambda kv: -kv[1])[:6])
+        assert not bad, f"fields outside 1e-9 relative (deviation / bar): {bad}"
     st = eng.episode_stats()
     assert st[0] == n_done
     eng.env_worst = env_worst
@@ -72,9 +118,18 @@ def _rollout_compare(E, O, dtype, n, steps, kw, seed, obs_tol, rew_tol, sample=N
     return worst_o, worst_r, n_done, eng
 
 
+# float64 bars.  Observations: 1e-9 relative with a floor of 1e-12 (normalised units; measured <= 7e-14 -- the old 2e-9 floor
+# was 1e-4 relative on dvartheta_int / 60 pi early in an episode); rewards 1e-10 (measured 2e-12: the CLASSIC reward reads
+# dvartheta_dt_dt, the 1/h^2-amplified signal, through exp(-0.4 |.| / |vref|)).
+F64_OBS_TOL = (1e-12, 1e-9)
+F64_REW_TOL = 1e-10
+
+
 def test_f64_matches_oracle_config2(E, oracle):
-    """BASELINE configs[1]: 4096 envs x 1000 env steps, float64, per-step parity of observation / reward / done."""
-    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F64, 4096, 1000, dict(), 5, (2e-9, 1e-9), 1e-9)
+    """BASELINE configs[1]: 4096 envs x 1000 env steps, float64, per-step parity of observation / reward / done AND of
+    the model itself: the 16 continuous states, every exported signal (stage-4 values) and the tick counter of every
+    env after every env step, within 1e-9 relative (dvartheta_dt_dt: 1e-9 + 1e-6 relative)."""
+    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F64, 4096, 1000, dict(), 5, F64_OBS_TOL, F64_REW_TOL, fields=True)
     assert nd == 4096 * 2  # two auto-resets per env in 1000 steps of 400-step episodes
     print(f"f64 4096x1000: max|dobs|={wo:.2e} max|drew|={wr:.2e}")
 
@@ -98,7 +153,7 @@ def test_f64_variants_match_oracle(E, oracle, name):
     kw = VARIANTS[name]
     steps = 320 if name == "K1_tk3" else 420
     # un-normalised observations carry raw magnitudes (Vx ~ 250): relative bar only
-    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F64, 512, steps, kw, 9, (2e-9, 1e-9), 1e-9)
+    wo, wr, nd, _ = _rollout_compare(E, oracle, E.F64, 512, steps, kw, 9, F64_OBS_TOL, F64_REW_TOL, fields=True)
     assert nd >= 512
     print(f"f64 {name}: max|dobs|={wo:.2e} max|drew|={wr:.2e} episodes={nd}")
 
