@@ -110,6 +110,7 @@ def _ref_worker(args):
     if dllref.available():
         env = O.RefEnv(cfg, env_id=wid)
         env.reset()
+        dllref.sandbox()  # this worker only computes from here on: no sockets, exec, ptrace or file writes (seccomp)
         run = lambda a: env.rollout(a, auto_reset=True, record=False)
     else:
         ob = O.OracleBatch(cfg, 1, env_id_offset=wid)

@@ -57,6 +57,15 @@ def lib():
     return _lib
 
 
+def sandbox():
+    """Drop what a numeric worker does not need before it runs the DLL in bulk (pe_host.c b747ref_sandbox: seccomp-bpf
+    deny-list -- sockets, exec, ptrace, module / mount calls, file writes).  Irrevocable for the calling process, so only
+    worker processes call it (bench.py's reference arm, the golden generators).  Returns True if the filter is installed."""
+    L = lib()
+    L.b747ref_sandbox.restype = ctypes.c_int
+    return L.b747ref_sandbox() == 0
+
+
 class DllModel:
     """One private instance of model_simple_win64.dll."""
 

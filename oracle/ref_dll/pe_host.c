@@ -17,6 +17,11 @@
  * file-default ISA flags (SSE2 path).  Exports are `void f(void)` and are
  * called through the Microsoft x64 ABI.
  *
+ * The DLL is an unaudited binary from the reference tree, so: the build refuses any file whose SHA-256 differs from the
+ * pinned one (oracle/Makefile, ref_dll/model_simple_win64.sha256); pages are never writable and executable at once
+ * (sections are laid out read-write, then code is re-protected read + execute and data loses execute); and the worker
+ * processes that run it in bulk drop network, exec, ptrace and file-write syscalls first (b747ref_sandbox, seccomp-bpf).
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may use this file's output (oracle/_ref/).
  */
@@ -26,6 +31,14 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <stddef.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <linux/audit.h>
+#include <linux/filter.h>
+#include <linux/seccomp.h>
+#include <sys/prctl.h>
+#include <sys/syscall.h>
 
 #ifndef B747_DLL_PATH
 #error "build with -DB747_DLL_PATH=\"/root/reference/core/model_simple_win64.dll\""
@@ -62,17 +75,20 @@ static inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); re
 static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
-b747ref_inst *b747ref_open(void) {
+/* Lay the embedded PE image out at `img` (page aligned, at least b747ref_image_size() bytes, readable + writable,
+ * zero-filled), apply the base relocations for that address, trap the imports, then tighten the page protections per
+ * section: code becomes read + execute, read-only data read-only, nothing is ever writable and executable at once. */
+static int load_image(uint8_t *img, b747ref_inst *in) {
   const uint8_t *file = b747ref_image_begin;
   size_t file_size = (size_t)(b747ref_image_end - b747ref_image_begin);
-  if (file_size < 0x400 || rd16(file) != 0x5a4d) return NULL;
+  if (file_size < 0x400 || rd16(file) != 0x5a4d) return -1;
   uint32_t nt = rd32(file + 0x3c);
-  if (rd32(file + nt) != 0x00004550) return NULL;
+  if (rd32(file + nt) != 0x00004550) return -1;
   const uint8_t *fh = file + nt + 4;      /* IMAGE_FILE_HEADER */
   uint16_t n_sections = rd16(fh + 2);
   uint16_t opt_size = rd16(fh + 16);
   const uint8_t *opt = fh + 20;           /* IMAGE_OPTIONAL_HEADER64 */
-  if (rd16(opt) != 0x20b) return NULL;    /* PE32+ only */
+  if (rd16(opt) != 0x20b) return -1;      /* PE32+ only */
   uint64_t preferred = rd64(opt + 24);
   uint32_t img_size = rd32(opt + 56);
   uint32_t hdr_size = rd32(opt + 60);
@@ -80,11 +96,6 @@ b747ref_inst *b747ref_open(void) {
   uint32_t exp_rva = rd32(dirs + 0 * 8);
   uint32_t imp_rva = rd32(dirs + 1 * 8);
   uint32_t rel_rva = rd32(dirs + 5 * 8), rel_size = rd32(dirs + 5 * 8 + 4);
-
-  uint8_t *img = mmap(NULL, img_size, PROT_READ | PROT_WRITE | PROT_EXEC,
-                      MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-  if (img == MAP_FAILED) return NULL;
-  b747ref_inst *in = calloc(1, sizeof *in);
   in->img = img; in->img_size = img_size; in->exp_rva = exp_rva;
 
   memcpy(img, file, hdr_size);
@@ -124,6 +135,38 @@ b747ref_inst *b747ref_open(void) {
       for (; *iat; iat++) *iat = (uint64_t)(uintptr_t)import_trap;
     }
   }
+  /* W^X: headers and read-only sections -> R, code -> R+X, writable data stays RW (never executable) */
+  mprotect(img, (hdr_size + 0xfff) & ~0xfffu, PROT_READ);
+  sec = opt + opt_size;
+  for (unsigned i = 0; i < n_sections; i++, sec += 40) {
+    uint32_t vsize = rd32(sec + 8), va = rd32(sec + 12), raw_size = rd32(sec + 16), flags = rd32(sec + 36);
+    uint32_t len = ((vsize ? vsize : raw_size) + 0xfff) & ~0xfffu;
+    int prot = PROT_READ;
+    if (flags & 0x20000000u) prot |= PROT_EXEC;        /* IMAGE_SCN_MEM_EXECUTE */
+    else if (flags & 0x80000000u) prot |= PROT_WRITE;  /* IMAGE_SCN_MEM_WRITE (a section that is both stays R+X) */
+    if (mprotect(img + va, len, prot)) return -2;
+  }
+  return 0;
+}
+
+uint32_t b747ref_image_size(void) {
+  const uint8_t *file = b747ref_image_begin;
+  uint32_t nt = rd32(file + 0x3c);
+  return rd32(file + nt + 4 + 20 + 56);
+}
+
+/* for the ELF face of the DLL (elf_shim.c): the image lives in the shim's own .bss */
+int b747ref_load_at(uint8_t *img, b747ref_inst *in) {
+  memset(in, 0, sizeof *in);
+  return load_image(img, in);
+}
+
+b747ref_inst *b747ref_open(void) {
+  uint32_t img_size = b747ref_image_size();
+  uint8_t *img = mmap(NULL, img_size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (img == MAP_FAILED) return NULL;
+  b747ref_inst *in = calloc(1, sizeof *in);
+  if (load_image(img, in)) { munmap(img, img_size); free(in); return NULL; }
   return in;
 }
 
@@ -167,3 +210,44 @@ void b747ref_state_load(b747ref_inst *in, const void *buf) {
   const uint8_t *b = buf;
   for (uint32_t i = 0; i < in->n_rw; i++) { memcpy(in->img + in->rw_rva[i], b, in->rw_size[i]); b += in->rw_size[i]; }
 }
+
+/* Worker-process sandbox (bench.py's reference-arm / cpu_baseline workers and the golden generators call it before they
+ * run the DLL): the import table is trapped, but unaudited machine code could still issue raw syscalls, so the process
+ * gives up -- irrevocably, seccomp-bpf -- everything a numeric loop does not need: no new sockets or connections, no
+ * exec, no ptrace / process_vm access, no module / bpf / mount calls, and files can only be opened read-only.  Pipes
+ * that are already open (the multiprocessing result channel) keep working.  Returns 0 on success. */
+#define DENY(nr) BPF_JUMP(BPF_JMP | BPF_JEQ | BPF_K, (nr), 0, 1), BPF_STMT(BPF_RET | BPF_K, SECCOMP_RET_ERRNO | EPERM)
+int b747ref_sandbox(void) {
+  struct sock_filter f[] = {
+      BPF_STMT(BPF_LD | BPF_W | BPF_ABS, offsetof(struct seccomp_data, arch)),
+      BPF_JUMP(BPF_JMP | BPF_JEQ | BPF_K, AUDIT_ARCH_X86_64, 1, 0),
+      BPF_STMT(BPF_RET | BPF_K, SECCOMP_RET_KILL_PROCESS),
+      BPF_STMT(BPF_LD | BPF_W | BPF_ABS, offsetof(struct seccomp_data, nr)),
+      DENY(SYS_socket), DENY(SYS_connect), DENY(SYS_bind), DENY(SYS_listen), DENY(SYS_accept), DENY(SYS_accept4),
+      DENY(SYS_execve), DENY(SYS_execveat), DENY(SYS_ptrace), DENY(SYS_process_vm_readv), DENY(SYS_process_vm_writev),
+      DENY(SYS_mount), DENY(SYS_umount2), DENY(SYS_pivot_root), DENY(SYS_chroot), DENY(SYS_init_module),
+      DENY(SYS_finit_module), DENY(SYS_delete_module), DENY(SYS_kexec_load), DENY(SYS_bpf), DENY(SYS_perf_event_open),
+      DENY(SYS_unlink), DENY(SYS_unlinkat), DENY(SYS_rename), DENY(SYS_renameat), DENY(SYS_renameat2), DENY(SYS_creat),
+      DENY(SYS_truncate), DENY(SYS_chmod), DENY(SYS_fchmodat), DENY(SYS_chown), DENY(SYS_fchownat), DENY(SYS_link),
+      DENY(SYS_linkat), DENY(SYS_symlink), DENY(SYS_symlinkat), DENY(SYS_mkdir), DENY(SYS_mkdirat), DENY(SYS_rmdir),
+      DENY(SYS_setuid), DENY(SYS_setgid), DENY(SYS_setreuid), DENY(SYS_setregid), DENY(SYS_setresuid), DENY(SYS_setresgid),
+      DENY(SYS_kill), DENY(SYS_tkill), DENY(SYS_tgkill),
+      /* open(path, flags) / openat(dirfd, path, flags): read-only opens only */
+      BPF_JUMP(BPF_JMP | BPF_JEQ | BPF_K, SYS_open, 0, 4),
+      BPF_STMT(BPF_LD | BPF_W | BPF_ABS, offsetof(struct seccomp_data, args[1])),
+      BPF_JUMP(BPF_JMP | BPF_JSET | BPF_K, O_WRONLY | O_RDWR | O_CREAT | O_TRUNC | O_APPEND, 0, 1),
+      BPF_STMT(BPF_RET | BPF_K, SECCOMP_RET_ERRNO | EPERM),
+      BPF_STMT(BPF_RET | BPF_K, SECCOMP_RET_ALLOW),
+      BPF_JUMP(BPF_JMP | BPF_JEQ | BPF_K, SYS_openat, 0, 4),
+      BPF_STMT(BPF_LD | BPF_W | BPF_ABS, offsetof(struct seccomp_data, args[2])),
+      BPF_JUMP(BPF_JMP | BPF_JSET | BPF_K, O_WRONLY | O_RDWR | O_CREAT | O_TRUNC | O_APPEND, 0, 1),
+      BPF_STMT(BPF_RET | BPF_K, SECCOMP_RET_ERRNO | EPERM),
+      BPF_STMT(BPF_RET | BPF_K, SECCOMP_RET_ALLOW),
+      BPF_STMT(BPF_RET | BPF_K, SECCOMP_RET_ALLOW),
+  };
+  struct sock_fprog prog = {(unsigned short)(sizeof f / sizeof f[0]), f};
+  if (prctl(PR_SET_NO_NEW_PRIVS, 1, 0, 0, 0)) return -1;
+  if (prctl(PR_SET_SECCOMP, SECCOMP_MODE_FILTER, &prog, 0, 0)) return -2;
+  return 0;
+}
+#undef DENY

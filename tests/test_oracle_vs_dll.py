@@ -153,3 +153,49 @@ def test_env_layer_restatement_tracks_dll(dllref, oracle):
         assert (d_d == d_c[1]).all(), name
         assert np.allclose(o_c[1], o_d, rtol=1e-8, atol=2e-9), name
         assert np.allclose(r_c[1], r_d, rtol=0, atol=2e-7 if cfg.rew_type == O.REW_CLASSIC else 1e-9), name
+
+
+def test_dll_host_never_maps_writable_and_executable(dllref, oracle):
+    """pe_host.c lays the image out read-write and then re-protects per section: no page of the hosted DLL (or of the
+    ELF face the reference's Python loads) is writable and executable at once."""
+    env = oracle.RefEnv(oracle.make_cfg(), env_id=0)
+    env.reset()
+    env.step(0.1)
+    rwx = [ln for ln in open("/proc/self/maps") if ln.split()[1].startswith("rwx")]
+    assert not rwx, rwx
+
+
+def _sandbox_child(q):
+    import numpy as np
+    from oracle import dllref as D, oracle as O
+    env = O.RefEnv(O.make_cfg(), env_id=0)
+    env.reset()
+    res = {"installed": D.sandbox()}
+    for what, fn in (("write", lambda: open("/tmp/b747_sandbox_probe", "w")),
+                     ("socket", lambda: __import__("socket").socket()),
+                     ("exec", lambda: __import__("os").execv("/bin/true", ["true"]))):
+        try:
+            fn()
+            res[what] = "allowed"
+        except OSError as e:
+            res[what] = e.errno
+    _, r, _ = env.rollout(np.zeros(400))
+    res["ret"] = float(r.sum())
+    q.put(res)
+
+
+def test_worker_sandbox_denies_io_but_runs_the_dll(dllref):
+    """bench.py's reference-arm workers call dllref.sandbox() before they run the DLL in bulk: file writes, sockets and
+    exec are refused (EPERM) from then on, the numeric path is unaffected (K7: a = 0 return 299.93)."""
+    import errno
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_sandbox_child, args=(q,))
+    p.start()
+    res = q.get(timeout=120)
+    p.join(30)
+    if not res["installed"]:
+        pytest.skip("seccomp filters cannot be installed in this container")
+    assert res["write"] == errno.EPERM and res["socket"] == errno.EPERM and res["exec"] == errno.EPERM
+    assert res["ret"] > 100
