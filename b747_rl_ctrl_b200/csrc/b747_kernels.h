@@ -31,6 +31,7 @@ struct StateF32 {
   int* last_len = nullptr;
   TraceState trace;  // recorder / step-response tracker (optional; routes the launch to the general kernel)
   float4* tables = nullptr;  // merged-axis look-up tables (b747_tables.h), ft::CELLS float4
+  unsigned int* tile_ctr = nullptr;  // 64 tile counters of the persistent step kernel (one per launch in flight)
 };
 
 int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t stream);

@@ -18,6 +18,7 @@
 // export as well (each feature left out of a tier is left out of its instruction footprint).  All are persistent-warp kernels: grid = SMs x resident blocks, tables staged once per block.
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "b747_kernels.h"
@@ -95,6 +96,10 @@ __device__ __forceinline__ void load_mx(const StateF32& st, size_t np, int i, Re
 // Selected per launch (launch_env_step32): on for K <= B747_STAGED_MAX_K substeps, where the step is HBM-latency bound
 // (measured round 1, 1 Mi envs: K=1 0.0737 -> 0.0715 ms), off above (K=2 0.090 vs 0.091 ms, K=10 0.283 vs 0.289 ms: the extra
 // shared-memory round trip costs issue slots the compute-bound regime does not have).
+#ifndef B747_L2_PREFETCH
+#define B747_L2_PREFETCH 0  // 1: next tile's state prefetched into L2 while the current one is stepped (measured round 2,
+                            // steady state K = 10: 0.2890 -> 0.2926 ms with it, 0.3150 -> 0.3189 with static tiles: rejected)
+#endif
 #ifndef B747_STAGED_MAX_K
 #define B747_STAGED_MAX_K 1
 #endif
@@ -273,7 +278,8 @@ template <int TIER, int SW = -1, bool STG = false, bool PFA = false>
 __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, const float* __restrict__ actions,
                                                     float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                     uint8_t* __restrict__ done_out, float* __restrict__ term_obs,
-                                                    float4* __restrict__ out4, uint32_t* __restrict__ done_bits) {
+                                                    float4* __restrict__ out4, uint32_t* __restrict__ done_bits,
+                                                    unsigned int* __restrict__ tile_ctr) {
   // Persistent warps: the launch fills the GPU once (blocks = SMs x resident blocks per SM), the tables are staged into
   // shared memory once per block, and every warp then walks its own stride of 32-env tiles with no block-level
   // synchronisation until the episode statistics are flushed at the very end.
@@ -299,10 +305,30 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
   uint32_t phase = 0;
   float a_next = 0.f;
   if ((STAGED || PFA) && wt0 < n_tiles && c.env_lo + wt0 * 32 + lane < c.env_hi) a_next = actions[c.env_lo + wt0 * 32 + lane];
+  // Tiles: the first one of every warp is fixed (wt0); the following ones are handed out by a global counter (tile_ctr)
+  // in completion order, so a warp whose envs took slow paths (table re-searches, libm fall-backs of tumbling airframes)
+  // does not hold a fixed share of the remaining work -- the static stride left the block barrier at the end of the
+  // kernel with 8 % of all stall samples (ncu r2g).  STAGED keeps the static stride (its next tile is already in flight).
+  const bool dyn = !STAGED && tile_ctr != nullptr;
 #pragma unroll 1
-  for (int wt = wt0; wt < n_tiles; wt += wstride) {
+  for (int wt = wt0; wt < n_tiles;) {
+  int wn = wt + wstride;
+  if (dyn) {
+    unsigned nx = 0;
+    if (lane == 0) nx = atomicAdd(tile_ctr, 1u);
+    wn = wstride + (int)__shfl_sync(0xffffffffu, nx, 0);
+  }
   const int i = c.env_lo + wt * 32 + lane;
   const bool live = i < c.env_hi;
+  if (B747_L2_PREFETCH && !STAGED && wn < n_tiles && (lane & 7) == 0) {
+    // the next tile's state on its way into L2 while this one is stepped: four 128-byte lines per 512-byte group
+    const int in = c.env_lo + wn * 32 + lane;
+    constexpr int ngd = GEN ? (CS ? 11 : 11) : 6, ngf = GEN ? 5 : 3;
+#pragma unroll
+    for (int g = 0; g < ngd; g++) asm volatile("prefetch.global.L2 [%0];" ::"l"(st.D + (size_t)g * np + in));
+#pragma unroll
+    for (int g = 0; g < ngf; g++) asm volatile("prefetch.global.L2 [%0];" ::"l"(st.F + (size_t)g * np + in));
+  }
   bool done = false;
   double ep_ret = 0.0, ep_len = 0.0;
   RegsMx r;
@@ -312,15 +338,14 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
     phase ^= 1;
     load_mx_staged(&sStage[STAGED ? warp : 0][0], lane, r);
     __syncwarp();  // every lane has read its slots: the buffer can take the next tile
-    const int wn = wt + wstride;
     if (wn < n_tiles) {
       if (lane == 0) stage_issue(st, np, c.env_lo + wn * 32, buf, bar);
       if (c.env_lo + wn * 32 + lane < c.env_hi) a_next = actions[c.env_lo + wn * 32 + lane];
     }
   }
   if (PFA && !STAGED) {
-    const int in = i + wstride * 32;
-    if (in < c.env_hi) a_next = actions[in];
+    const int in = c.env_lo + wn * 32 + lane;
+    if (wn < n_tiles && in < c.env_hi) a_next = actions[in];
   }
   if (live) {
     if (!STAGED) {
@@ -507,6 +532,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
     if (lane == 0) done_bits[(c.env_lo >> 5) + wt] = b;
   }
   warp_episode_stats(s_stats, done, ep_ret, ep_len);
+  wt = wn;
   }
   __syncthreads();
   if (threadIdx.x < 4 && s_stats[threadIdx.x] != 0.0) atomicAdd(st.stats + threadIdx.x, s_stats[threadIdx.x]);
@@ -596,6 +622,7 @@ int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t st
             cudaMalloc(&s.last_ret, sizeof(double) * np) == cudaSuccess &&
             cudaMalloc(&s.last_len, sizeof(int) * np) == cudaSuccess &&
             cudaMalloc(&s.tables, sizeof(float4) * ft::CELLS) == cudaSuccess &&
+            cudaMalloc(&s.tile_ctr, sizeof(unsigned int) * 64) == cudaSuccess &&
             cudaMemcpy(s.tables, F.v.data(), sizeof(float4) * ft::CELLS, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) {  // release whatever was allocated: a retry with fewer envs must find the HBM free
     const cudaError_t e = cudaGetLastError();
@@ -610,12 +637,16 @@ int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t st
 }
 
 void f32_free(StateF32& s) {
-  cudaFree(s.D); cudaFree(s.F); cudaFree(s.sig); cudaFree(s.stats); cudaFree(s.last_ret); cudaFree(s.last_len); cudaFree(s.tables);
+  cudaFree(s.D); cudaFree(s.F); cudaFree(s.sig); cudaFree(s.stats); cudaFree(s.last_ret); cudaFree(s.last_len); cudaFree(s.tables); cudaFree(s.tile_ctr);
   s = StateF32{};
 }
 
 static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 
+#ifndef B747_DYNAMIC_TILES
+#define B747_DYNAMIC_TILES 1  // 0: static tile stride per warp
+#endif
+constexpr int kTileCtrSlots = 64;
 #ifndef B747_PERSISTENT
 #define B747_PERSISTENT 1  // 0: one 128-env tile per block (grid = all tiles)
 #endif
@@ -652,9 +683,18 @@ void launch_env_step32(const DevCfg& c, const StateF32& st, const float* actions
   const int n = c.env_hi - c.env_lo;
   if (n <= 0) return;
   const bool plain = !st.trace.trk && !st.trace.rec && !st.sig && !c.force_full;
+  // tile counter of this launch: one of kTileCtrSlots words, zeroed on the launch stream (launches of one handle may
+  // overlap on different streams -- b747_step_host's chunk pipeline -- so consecutive launches take different slots)
+  unsigned int* ctr = nullptr;
+  const bool staged = plain && f32_is_lean(c) && mp.sw == SW_RP && !prefetch_actions && c.substeps <= B747_STAGED_MAX_K;
+  if (st.tile_ctr && B747_DYNAMIC_TILES && !staged) {
+    static std::atomic<unsigned> seq{0};
+    ctr = st.tile_ctr + (seq.fetch_add(1) % kTileCtrSlots);
+    cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s);
+  }
 #define B747_LAUNCH(TIER, ...) \
   k_env_step32<TIER, ##__VA_ARGS__><<<step_grid<TIER, ##__VA_ARGS__>(n), TIER == 0 ? B747_F32_THREADS : 128, 0, s>>>( \
-      c, mp, st, actions, obs, rew, done, term_obs, out4, done_bits)
+      c, mp, st, actions, obs, rew, done, term_obs, out4, done_bits, ctr)
   if (plain && f32_is_lean(c) && mp.sw == SW_RP && prefetch_actions)  // host-mapped action buffer (b747_step_host_packed)
     B747_LAUNCH(0, SW_RP, false, true);
   else if (plain && f32_is_lean(c) && mp.sw == SW_RP && c.substeps <= B747_STAGED_MAX_K)  // HBM-bound regime: TMA-staged state

@@ -4,6 +4,7 @@ import ctypes
 import json
 import math
 import os
+import sys
 import random
 import shutil
 import tempfile
@@ -13,6 +14,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
 DEG = math.pi / 180
 
 

@@ -11,11 +11,14 @@ tests/golden/make_env_golden_refpy.py, provenance line inside the file).  Checke
 """
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
 
 
 def _golden():
