@@ -333,7 +333,13 @@ def run_cuda(args, rank, local_rank, world):
     # clock samples need >= 0.5 s under load (nvidia-smi samples every 100 ms; 20 steps last 6 ms): the same timed pass is
     # repeated, the sampler keeps running across the timed region and the repeats, the repeats' spread is reported
     rep_ms = [ms_total / args.steps]
-    while time.time() - t_wall0 < 0.7 and len(rep_ms) < 2000:
+    # the number of repeats is derived from the max-over-ranks time of the first pass, so every rank runs the SAME number
+    # of barriers (a per-rank wall-clock loop dead-locks the ranks against each other)
+    t_first = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_first, op=dist.ReduceOp.MAX)
+    n_rep = int(min(500, max(1, math.ceil(700.0 / max(float(t_first.item()), 1e-3)))))
+    for _ in range(n_rep):
         m, _ = timed_pass(eng, args.steps)
         rep_ms.append(m / args.steps)
     t_wall1 = time.time()
