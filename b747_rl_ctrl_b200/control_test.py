@@ -29,8 +29,8 @@ def _enum(x, default=None):
 def run_control_test(policy=None, vartheta_ref=DEFAULT_REFS, state0=DEFAULT_STATE0, *, observation_type=E.OBS_PID_LIKE,
                      reward_type=E.REW_CLASSIC, norm_obs=True, norm_act=True, ctrl_mode=E.MODE_DIRECT, ctrl_type=E.CTRL_MANUAL,
                      tk=20.0, sample_time=0.05, action_max=17 * DEG, vartheta_max=10 * DEG, use_limiter=False,
-                     aero_err=None, disturbance_mode=None, reward_config=None, pid_ss=None, h_ref=None, dtype=E.F64,
-                     device=0, record=False, max_steps=None):
+                     aero_err=None, disturbance_mode=None, reward_config=None, pid_ss=None, pid_cs=None, h_ref=None,
+                     dtype=E.F64, device=0, record=False, max_steps=None):
     """One deterministic episode per reference value, all in one batch.
 
     policy: callable(obs[n, obs_dim] float array) -> actions[n] (or [n, 1]); None -> zero actions, i.e. the pure
@@ -52,6 +52,8 @@ def run_control_test(policy=None, vartheta_ref=DEFAULT_REFS, state0=DEFAULT_STAT
     try:
         if pid_ss is not None:
             eng.set_param("PID_SS", np.asarray(pid_ss, np.float64))
+        if pid_cs is not None:
+            eng.set_param("PID_CS", np.asarray(pid_cs, np.float64))
         use_ctrl = _enum(ctrl_type) in (E.CTRL_SEMI_MANUAL, E.CTRL_FULL_AUTO)
         eps = [E.episode(state0, vref=(0.0 if h_ref is not None else r), h_ref=(r if h_ref is not None else 11000.0),
                          use_ctrl=use_ctrl, aero_err=aero_err) for r in refs]
@@ -112,3 +114,59 @@ class ControlTest:
             self.best_mean_quality = self.mean_quality
         log['improved'] = improved
         return log
+
+
+# ---- ControllerAgent.test (neural/agent.py:235-409): PID baselines beside the trained policies -------------------------
+TABLE_COLUMNS = ('Устройство', 'σ, [%]', 'tпп, [с]', 'tв, [с]', 'Δ', 'Q, [-]')   # the reference's DataFrame columns
+
+
+def run_agent_test(ref_values, policies=None, state0=DEFAULT_STATE0, *, ctrl_type=E.CTRL_MANUAL, pid_coefs=(),
+                   no_neural=False, **env_kwargs):
+    """The comparison `ControllerAgent.test` prints and writes to xlsx, as plain tables, every episode of a device in one
+    batch.
+
+    For every reference value (pitch references in rad for CtrlType.MANUAL, altitude references in m for SEMI_MANUAL --
+    the reference switches on `env.ctrl.use_ctrl`, agent.py:250-253) one row per device:
+      * the PID baseline(s): the same loop with the СС PID in place of the network -- ctrl_type AUTO (from MANUAL) or
+        FULL_AUTO (from SEMI_MANUAL), no action law, sample_time = dt, tk / dt interactions (agent.py:300-307, 342-344);
+        `pid_coefs` = alternative coefficient sets, written to PID_SS or PID_CS (agent.py:292-297);
+      * every policy of `policies` ({name: callable(obs[n, obs_dim]) -> actions[n]}), deterministic, on its own env
+        configuration (`env_kwargs`, shared by all policies here), tk / sample_time interactions.
+    A row = overshoot [%], settling time, rise time, static error (calc_stepinfo of the pitch angle or the altitude,
+    stepinfo_SS / stepinfo_CS) and Controller.quality().  Returns {"tables": {ref: [rows]}, "mean": [rows]}: `mean` is
+    the reference's data_*_info_mean table -- |overshoot| first, then the mean over the reference values per device.
+    """
+    ctrl_type = _enum(ctrl_type)
+    use_ctrl = ctrl_type in (E.CTRL_SEMI_MANUAL, E.CTRL_FULL_AUTO)
+    pid_type = E.CTRL_FULL_AUTO if use_ctrl else E.CTRL_AUTO
+    refs = [float(v) for v in ref_values]
+    base_name = "CУ ПИД" if use_ctrl else "СС ПИД"
+    coef_sets = [np.asarray(c, np.float64) for c in pid_coefs] or [None]
+    which = dict(h_ref=refs) if use_ctrl else dict(vartheta_ref=refs)
+    devices = []   # (name, result dict with one entry per reference)
+    pid_kw = {k: v for k, v in env_kwargs.items() if k not in ("ctrl_mode", "sample_time", "observation_type", "reward_type")}
+    for i, coefs in enumerate(coef_sets):
+        name = base_name + (f" [{i + 1}]" if len(coef_sets) > 1 else "")
+        kw = dict(pid_kw, ctrl_type=pid_type, ctrl_mode=E.MODE_DIRECT, sample_time=None)
+        if coefs is not None:
+            kw["pid_cs" if use_ctrl else "pid_ss"] = coefs
+        devices.append((name, run_control_test(None, state0=state0, **which, **kw)))
+    if not no_neural:
+        for name, policy in (policies or {}).items():
+            devices.append((name, run_control_test(policy, state0=state0, ctrl_type=ctrl_type, **which, **env_kwargs)))
+    unit = 'Δ, [м]' if use_ctrl else 'Δ, [град]'
+
+    def row(name, r, j):
+        val = lambda x: None if x != x else float(x)
+        return {'Устройство': name, 'σ, [%]': val(r["overshoot"][j]), 'tпп, [с]': val(r["settling_time"][j]),
+                'tв, [с]': val(r["rise_time"][j]), unit: val(r["static_error"][j]), 'Q, [-]': val(r["quality"][j])}
+    tables = {ref: [row(name, r, j) for name, r in devices] for j, ref in enumerate(refs)}
+    mean = []
+    for name, r in devices:
+        m = {'Устройство': name}
+        for col, key, absolute in (('σ, [%]', "overshoot", True), ('tпп, [с]', "settling_time", False),
+                                   ('tв, [с]', "rise_time", False), (unit, "static_error", False), ('Q, [-]', "quality", False)):
+            v = np.abs(r[key]) if absolute else r[key]
+            m[col] = float(np.nanmean(v)) if np.isfinite(v).any() else None
+        mean.append(m)
+    return {"tables": tables, "mean": mean, "unit": unit}

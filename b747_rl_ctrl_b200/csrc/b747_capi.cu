@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -36,6 +37,11 @@ struct b747_handle {
   float4* d_out4 = nullptr;      // packed outputs of b747_step_host_packed (pageable / copy modes), allocated on first use
   uint32_t* d_bits = nullptr;    // done flags, one bit per env
   int host_mode = -1;            // b747_step_host_packed: -1 automatic, 0 copy pipeline, 1 zero-copy outputs, 2 zero-copy both ways
+  // automatic mode: the first calls alternate between zero-copy (2) and staged copies (0) and are timed; the faster one is
+  // kept.  Alone on the host link zero-copy wins (2.7e9 against 2.2e9 env-steps/s at 1 Mi envs); with eight GPUs sharing
+  // it the copy engines hold the link better (7.3e9 against 6.8e9, profiles/r2_hostlink_probe.md).  Results are identical.
+  int auto_calls = 0, auto_choice = -1;
+  double auto_sec[2] = {0.0, 0.0};
   // b747_step_host pipeline: copy-in / second compute / copy-out streams and per-chunk events (created on first use)
   cudaStream_t s_in = nullptr, s_aux = nullptr, s_out = nullptr, s_cap = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_k;
@@ -546,6 +552,7 @@ extern "C" int b747_step_packed(b747_handle* h, const float* act_dev, float* out
 extern "C" int b747_set_host_mode(b747_handle* h, int mode) {
   if (!h || mode < -1 || mode > 2) return fail(B747_ERR_ARG, "mode must be -1 (automatic), 0, 1 or 2");
   h->host_mode = mode;
+  h->auto_calls = 0; h->auto_choice = -1; h->auto_sec[0] = h->auto_sec[1] = 0.0;
   return B747_OK;
 }
 
@@ -567,9 +574,27 @@ extern "C" int b747_step_host_packed(b747_handle* h, const float* act, float* ou
   float* m_act = (float*)mapped_ptr(act);
   float4* m_out = (float4*)mapped_ptr(out4);
   int mode = h->host_mode;
-  if (mode < 0) mode = 2;
+  const bool can_map = m_out && m_act && is_pinned(done_bits);
+  bool calibrating = false;
+  if (mode < 0) {
+    mode = 2;
+    if (can_map && n >= ((size_t)1 << 17)) {  // small batches: launch-bound either way, zero-copy has fewer operations
+      if (h->auto_choice >= 0) mode = h->auto_choice;
+      else { calibrating = true; mode = (h->auto_calls & 1) ? 0 : 2; }
+    }
+  }
   if (!m_out || !is_pinned(done_bits)) mode = 0;
   if (mode == 2 && !m_act) mode = 1;
+  const auto t_begin = std::chrono::steady_clock::now();
+  struct Calib {  // on every return path: book the call's time and decide after 4 + 4 calls (the first pair is warm-up)
+    b747_handle* h; bool on; int mode; std::chrono::steady_clock::time_point t0;
+    ~Calib() {
+      if (!on) return;
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (h->auto_calls >= 2) h->auto_sec[mode == 0 ? 1 : 0] += dt;
+      if (++h->auto_calls >= 10) h->auto_choice = h->auto_sec[1] < 0.95 * h->auto_sec[0] ? 0 : 2;
+    }
+  } calib{h, calibrating, mode, t_begin};
   if (mode >= 1) {
     // Zero-copy: the kernel stores each env's float4 straight into the caller's pinned buffer -- 512 contiguous bytes per
     // warp, posted PCIe writes that overlap the stepping of the other tiles -- and (mode 2) fetches the actions from the

@@ -3,9 +3,14 @@
 The reference trains `PPO('MlpPolicy', env)` from stable-baselines3 1.4.0 with default hyper-parameters on
 `SubprocVecEnv([env] * 4)` (neural/agent.py:46-81; setups.py's dict never matches, so the defaults apply): 2 x 64 tanh
 MLPs for policy and value, state-independent log-std, Adam(3e-4, eps 1e-5), gamma 0.99, GAE lambda 0.95, clip 0.2,
-vf_coef 0.5, max_grad_norm 0.5, advantage normalisation, 10 epochs.  stable-baselines3 is not installed in this image,
-so the algorithm is restated here in plain torch with those defaults; what changes with 65536 environments is the
-rollout geometry only (n_steps x n_envs samples per update and the minibatch size), which are arguments.
+vf_coef 0.5, max_grad_norm 0.5, advantage normalisation, n_steps 2048, batch 64, 10 epochs.  stable-baselines3 is not
+installed in this image, so the algorithm is restated here in plain torch.  The loss, the optimiser and the network
+are SB3's defaults; the ROLLOUT GEOMETRY is not, and `train()`'s own defaults say so: with 65536 environments one
+update already holds n_steps x n_envs = 32 x 65536 = 2 Mi samples (SB3: 2048 x 4 = 8192), cut into 16 minibatches of
+128 Ki (SB3: 128 minibatches of 64) for 4 epochs (SB3: 10).  Every call reports the values it used under "hyper" in
+its result, and `ep_rew_mean` is the mean over the episodes that finished during the last update (episode phases are
+spread first), so "steps / seconds to ep_rew_mean 225" is a statement about this geometry, not a like-for-like replay
+of the reference's 4-env run.
 
 Observations, actions, rewards and dones never leave HBM: the environment step is one launch of k_env_step32 on
 torch's current stream, the policy is a torch module on the same device.  Episodes end by the time limit and are
@@ -57,7 +62,8 @@ def _log_prob(a, mean, log_std):
 def train(n_envs=65536, total_steps=None, threshold=225.0, max_seconds=600.0, n_steps=32, n_minibatches=16, n_epochs=4,
           lr=3e-4, gamma=0.99, gae_lambda=0.95, clip=0.2, vf_coef=0.5, ent_coef=0.0, max_grad_norm=0.5, seed=1, device=0,
           env_kwargs=None, log=None, desync=True, use_graphs=True, tf32=True):
-    """PPO with SB3's defaults.  use_graphs: the T-step rollout (policy, sampling, env kernel, GAE) and one epoch of
+    """PPO with SB3's loss / optimiser / network defaults on a rollout geometry sized for 10^4..10^5 environments (module
+    docstring; the values used are returned under "hyper").  use_graphs: the T-step rollout (policy, sampling, env kernel, GAE) and one epoch of
     minibatch updates are each captured ONCE as a CUDA graph and replayed -- the eager form spends 98 % of a rollout step
     in launch overhead of ~30 tiny policy kernels around a 0.02 ms environment step."""
     torch.manual_seed(seed)
@@ -203,7 +209,10 @@ def train(n_envs=65536, total_steps=None, threshold=225.0, max_seconds=600.0, n_
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     eng.close()
-    return dict(steps=steps_done, seconds=wall, steps_per_s=steps_done / wall, updates=updates, history=history,
+    hyper = dict(n_envs=n_envs, n_steps=n_steps, n_minibatches=n_minibatches, minibatch_size=mb, n_epochs=n_epochs, lr=lr,
+                 gamma=gamma, gae_lambda=gae_lambda, clip=clip, vf_coef=vf_coef, ent_coef=ent_coef, max_grad_norm=max_grad_norm,
+                 sb3_defaults=dict(n_envs=4, n_steps=2048, minibatch_size=64, n_epochs=10), tf32=tf32, desync=desync)
+    return dict(steps=steps_done, seconds=wall, steps_per_s=steps_done / wall, updates=updates, history=history, hyper=hyper,
                 threshold=threshold, reached=(None if t_hit is None else dict(seconds=t_hit[0], steps=t_hit[1], ep_rew_mean=t_hit[2])),
                 final_ep_rew_mean=(history[-1][2] if history else None), net=net, graphs=g_roll is not None)
 

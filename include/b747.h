@@ -136,8 +136,10 @@ int b747_set_host_chunks(b747_handle *h, int n_chunks);
  * writes of 512 contiguous bytes per warp that overlap the stepping of the other envs); pageable buffers are staged. */
 int b747_step_packed(b747_handle *h, const float *actions_dev, float *out4_dev, uint32_t *done_bits_dev);
 int b747_step_host_packed(b747_handle *h, const float *actions, float *out4, uint32_t *done_bits);
-/* Host path of b747_step_host_packed with page-locked buffers: -1 automatic (2), 0 staged copies (chunk pipeline),
- * 1 actions copied / records stored zero-copy, 2 actions and records zero-copy. */
+/* Host path of b747_step_host_packed with page-locked buffers: 0 staged copies (chunk pipeline), 1 actions copied /
+ * records stored zero-copy, 2 actions and records zero-copy, -1 automatic (default): the first ten calls alternate
+ * between 2 and 0 and are timed, the faster path is kept (zero-copy when the GPU has the host link to itself, staged
+ * copies when many GPUs share it).  Results are identical in every mode. */
 int b747_set_host_mode(b747_handle *h, int mode);
 /* env.seed(s) of the gym / SB3 API (neural/agent.py:80): re-keys the Philox stream used by every later random reset. */
 int b747_set_seed(b747_handle *h, uint64_t seed);

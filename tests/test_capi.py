@@ -42,6 +42,16 @@ def test_scalar_abi_symbols(libs):
             "state0": 6, "h_zh": 1, "use_RP": 1, "use_PID_SS": 1, "use_PID_CS": 1, "PID_SS": 4, "PID_CS": 4,
             "deltaz": 1, "vartheta": 1, "P": 1, "aero_err": 5, "Iz": 1, "S": 1, "c_": 1, "g": 1, "m0": 1, "use_RL": 1,
             "alpha": 1, "V": 1, "Mach": 1}
+    # where the reference tree is mounted, the list comes from core/model.py itself: every `in_dll(self.dll, "<name>")`
+    ref_model = "/root/reference/core/model.py"
+    if os.path.exists(ref_model):
+        src = open(ref_model, encoding="utf-8").read()
+        bound = re.findall(r"""(\(real_T\*(\d+)\)|real_T)\.in_dll\(self\.dll,\s*['"](\w+)['"]\)""", src)
+        assert len(bound) >= 34
+        for _, n_elem, name in bound:
+            assert data.get(name) == int(n_elem or 1), f"core/model.py binds {name}[{n_elem or 1}]"
+        funcs = set(re.findall(r"""getattr\(self\.dll,\s*f["']\{model\}_(\w+)["']\)""", src))
+        assert funcs == {"initialize", "step", "terminate"}
     for n, k in data.items():
         v = (ctypes.c_double * k).in_dll(scal, n)
         assert len(v) == k

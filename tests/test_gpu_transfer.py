@@ -149,3 +149,46 @@ def test_controller_facade_storage_and_stepinfo(E):
     for k in NAMES:
         assert info_b[k] == pytest.approx(g["stepinfo"][k], rel=1e-8, abs=1e-10), k
     env.close()
+
+
+def test_agent_test_tables_pid_beside_policy(E, oracle):
+    """ControllerAgent.test (neural/agent.py:268-409): for every reference value a table with the PID baseline (СС PID in
+    the loop, sample_time = dt) beside the policy, and the mean table over the references.  The PID rows are checked
+    against the oracle running the same loop (ctrl_type AUTO, K = 1) with the reference's recorder + calc_stepinfo; a
+    zero policy in ADD_PROC mode must reproduce the published transfer numbers."""
+    from b747_rl_ctrl_b200.control_test import run_agent_test
+    refs = [d * DEG for d in DEGS]
+    out = run_agent_test(refs, {"zero_addproc": lambda obs: np.zeros(len(obs))}, ctrl_mode=E.MODE_ADD_PROC, action_max=1.0,
+                         pid_coefs=[[-5.9151, -1.2404, -6.6927, 58.0826], [-4.0, -1.0, -5.0, 58.0826]])
+    assert [r["Устройство"] for r in out["tables"][refs[0]]] == ["СС ПИД [1]", "СС ПИД [2]", "zero_addproc"]
+    cfg = oracle.make_cfg(ctrl_type=oracle.CTRL_AUTO, reset_ref_mode=oracle.RESET_NONE, sample_time=None, norm_act=True)
+    ob = oracle.OracleBatch(cfg, len(refs))
+    ob.reset_to([oracle.episode([0, 11000, 250, 0, 0, 0], vref=r) for r in refs])
+    views = [ob.env(i) for i in range(len(refs))]
+    for v in views:
+        v.enable_storage(2001)
+    for k in range(2000):
+        _, _, d, _ = ob.step(np.zeros(len(refs)), auto_reset=False)
+    assert d.all()
+    for j, ref in enumerate(refs):
+        info = views[j].stepinfo_SS()
+        row = out["tables"][ref][0]                     # default coefficients
+        assert row["σ, [%]"] == pytest.approx(info["overshoot"], rel=1e-8)
+        assert row["tпп, [с]"] == pytest.approx(info["settling_time"], abs=1e-9)
+        assert row["tв, [с]"] == pytest.approx(info["rise_time"], abs=1e-9)
+        assert row["Δ, [град]"] == pytest.approx(info["static_error"], rel=1e-7, abs=1e-10)
+        assert 0 < row["Q, [-]"] < 1
+        nn = out["tables"][ref][2]
+        g = GOLD[str(DEGS[j])]
+        assert nn["σ, [%]"] == pytest.approx(g["stepinfo"]["overshoot"], rel=1e-8) and nn["Q, [-]"] == pytest.approx(g["quality"], rel=1e-9)
+        assert out["tables"][ref][1]["σ, [%]"] != row["σ, [%]"]   # the second coefficient set really is another controller
+    mean = {m["Устройство"]: m for m in out["mean"]}
+    assert mean["zero_addproc"]["σ, [%]"] == pytest.approx(9.263, abs=1e-3)
+    assert mean["zero_addproc"]["Q, [-]"] == pytest.approx(0.7527, abs=5e-5)
+    assert mean["СС ПИД [1]"]["σ, [%]"] == pytest.approx(np.mean([abs(out["tables"][r][0]["σ, [%]"]) for r in refs]))
+    # altitude references through the СУ PID (stepinfo_CS): FULL_AUTO baseline, no policy
+    alt = run_agent_test([10500.0, 11500.0], ctrl_type=E.CTRL_SEMI_MANUAL, no_neural=True, tk=60.0)
+    assert alt["unit"] == "Δ, [м]" and [r["Устройство"] for r in alt["tables"][10500.0]] == ["CУ ПИД"]
+    for ref in (10500.0, 11500.0):
+        r = alt["tables"][ref][0]
+        assert r["Δ, [м]"] is not None and r["Δ, [м]"] < 60.0 and r["tв, [с]"] is not None
