@@ -91,6 +91,7 @@ def load():
     L.b747_set_field.argtypes = [vp, c_int, vp]
     L.b747_episode_stats.argtypes = [vp, c_dp]
     L.b747_last_episode.argtypes = [vp, vp, vp]
+    L.b747_last_episode_of.argtypes = [vp, vp, ctypes.c_int32, vp, vp]
     L.b747_launch_count.restype = ctypes.c_int64
     L.b747_launch_count.argtypes = [vp]
     L.b747_synchronize.argtypes = [vp]

@@ -793,6 +793,41 @@ extern "C" int b747_episode_stats(b747_handle* h, double out[4]) {
   return B747_OK;
 }
 
+// Return / length of the most recently finished episode of SOME envs (the ones that just reported done): the
+// VecMonitor record of a step costs a few kilobytes instead of two whole-batch copies.
+__global__ void k_gather_last_episode(const double* __restrict__ ret, const int* __restrict__ len,
+                                      const int32_t* __restrict__ idx, int n_idx, double* __restrict__ out_ret,
+                                      int32_t* __restrict__ out_len) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_idx) return;
+  out_ret[k] = ret[idx[k]];
+  out_len[k] = len[idx[k]];
+}
+
+extern "C" int b747_last_episode_of(b747_handle* h, const int32_t* idx, int32_t n_idx, double* ret, int32_t* len) {
+  if (!h || !idx || !ret || !len || n_idx < 0) return fail(B747_ERR_ARG, "bad argument");
+  if (n_idx == 0) return B747_OK;
+  if (n_idx > h->cfg.n_envs) return fail(B747_ERR_ARG, "more indices than environments");
+  for (int32_t k = 0; k < n_idx; k++)
+    if (idx[k] < 0 || idx[k] >= h->cfg.n_envs) return fail(B747_ERR_ARG, "env index out of range");
+  CU(cudaSetDevice(h->cfg.device));
+  // staging: the handle's per-env scratch (d_eps holds n_pad episode descriptors of 152 bytes: room for idx, ret and len)
+  char* scratch = (char*)h->d_eps;
+  int32_t* d_idx = (int32_t*)scratch;
+  double* d_ret = (double*)(scratch + sizeof(double) * (size_t)h->dc.n_pad);
+  int32_t* d_len = (int32_t*)(scratch + 2 * sizeof(double) * (size_t)h->dc.n_pad);
+  CU(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n_idx, cudaMemcpyHostToDevice, h->stream));
+  const double* lr = h->cfg.dtype == B747_F64 ? h->s64.last_ret : h->s32.last_ret;
+  const int* ll = h->cfg.dtype == B747_F64 ? h->s64.last_len : h->s32.last_len;
+  k_gather_last_episode<<<(n_idx + 255) / 256, 256, 0, h->stream>>>(lr, ll, d_idx, n_idx, d_ret, d_len);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ret, d_ret, sizeof(double) * n_idx, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(len, d_len, sizeof(int32_t) * n_idx, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B747_OK;
+}
+
 extern "C" int b747_last_episode(b747_handle* h, double* ret, int32_t* len) {
   if (!h || !ret || !len) return fail(B747_ERR_ARG, "null argument");
   CU(cudaSetDevice(h->cfg.device));

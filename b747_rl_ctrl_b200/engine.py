@@ -249,6 +249,14 @@ class BatchEngine:
         check(self._L.b747_episode_stats(self._h, out))
         return np.array(out)
 
+    def last_episode_of(self, idx):
+        """(return, length) of the most recently finished episode of the envs `idx` (VecMonitor's record of a step)."""
+        idx = np.ascontiguousarray(idx, np.int32)
+        ret = np.empty(len(idx), np.float64)
+        ln = np.empty(len(idx), np.int32)
+        check(self._L.b747_last_episode_of(self._h, _ptr(idx), len(idx), _ptr(ret), _ptr(ln)))
+        return ret, ln
+
     def last_episode(self):
         ret = np.empty(self.n_envs, np.float64)
         ln = np.empty(self.n_envs, np.int32)

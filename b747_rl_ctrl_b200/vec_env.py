@@ -391,13 +391,13 @@ class B747VecEnv(_VecEnvBase):
 
     def _infos_idx(self, idx, rows):
         infos = list(self._no_infos)
-        ret, ln = self.engine.last_episode() if self.monitor else (None, None)
+        ret, ln = self.engine.last_episode_of(idx) if self.monitor else (None, None)   # only the finished envs' records
         t = round(time.time() - self._t0, 6)
         dev = hasattr(rows, "cpu")
         for j, i in enumerate(idx):
             info = {"terminal_observation": rows[j].clone() if dev else rows[j]}
             if self.monitor:
-                info["episode"] = {"r": float(ret[i]), "l": int(ln[i]), "t": t}
+                info["episode"] = {"r": float(ret[j]), "l": int(ln[j]), "t": t}
             infos[i] = info
         return infos
 

@@ -410,7 +410,7 @@ def run_cuda(args, rank, local_rank, world):
             e1 = E.BatchEngine(n_envs=n_local, dtype=E.F32, device=local_rank, sample_time=Kx * 0.01, seed=1, auto_reset=True)
             e1.use_stream(torch.cuda.current_stream().cuda_stream)
             e1.reset(obs)
-            _desync(e1, torch, n_local, min(int(round(20.0 / (Kx * 0.01))), 400), pool, obs, rew, done, dev)
+            _desync(e1, torch, n_local, int(round(20.0 / (Kx * 0.01))), pool, obs, rew, done, dev)
             for i in range(5):
                 e1.step(pool[i % 8], obs, rew, done)
             n1 = max(20, min(args.steps, 200))
@@ -490,12 +490,17 @@ def _vecenv_rate(n, K, device):
         env = B747VecEnv(n, sample_time=K * 0.01, device=device, copy_outputs=copy)
         env.reset()
         ep_len = int(round(20.0 / (K * 0.01)))
-        # spread the phases with masked resets so that episodes finish inside the timed steps
+        # spread the episode phases on the device (masked resets while stepping) so that ~1/ep_len of the envs finish --
+        # terminal observations, monitor records and info dicts included -- in every timed step
         import torch
-        ids = torch.arange(n, device=torch.device("cuda", device))
-        for t in range(0, ep_len, 4):
-            env.engine.reset(mask=((ids % ep_len) // 4 == t // 4).to(torch.uint8))
-            env.step(acts[t % 4])
+        dev = torch.device("cuda", device)
+        ids = torch.arange(n, device=dev)
+        a_d, o_d, r_d, d_d = env.engine.alloc_io()
+        for t in range(ep_len):
+            env.engine.step(a_d, o_d, r_d, d_d)
+            env.engine.reset(mask=((ids % ep_len) == t).to(torch.uint8))
+        env.engine.synchronize()
+        del a_d, o_d, r_d, d_d
         for i in range(3):
             env.step(acts[i % 4])
         steps, finished = 10, 0

@@ -170,6 +170,8 @@ int b747_set_field(b747_handle *h, int field, const double *in_host);
 int b747_episode_stats(b747_handle *h, double out_host[4]);
 /* Per-env return/length of the most recently finished episode (VecMonitor's infos[i]["episode"]). */
 int b747_last_episode(b747_handle *h, double *ret_host, int32_t *len_host);
+/* The same for n_idx chosen envs (idx_host[k] in [0, n_envs)): ret_host[k], len_host[k] of env idx_host[k]. */
+int b747_last_episode_of(b747_handle *h, const int32_t *idx_host, int32_t n_idx, double *ret_host, int32_t *len_host);
 
 /* Step-response metrics (handles created with track_transfer): out_host[n_envs][5] = overshoot [%], rise time [s],
  * settling time [s], static error, Controller.quality() -- calc_stepinfo's definitions (5 % band, times relative to
