@@ -10,6 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B747_LIB_PATH") or os.path.join(HERE, "lib", "libb747_b200.so")
 SCALAR_LIB_PATH = os.path.join(HERE, "lib", "model_simple.so")
+LEGACY_LIB_PATH = os.path.join(HERE, "lib", "model.so")   # boundary of the legacy core/model_win64.dll
 
 ABI_VERSION = 2
 OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_STATE = 0, -1, -2, -3, -4

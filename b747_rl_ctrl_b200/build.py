@@ -3,6 +3,7 @@
   lib/libb747_b200.so  the batched C ABI (include/b747.h)
   lib/model_simple.so  the reference's scalar boundary (include/b747_scalar.h), self-contained so
                        that it can be copied per Model instance like the reference does
+  lib/model.so         the boundary of the legacy core/model_win64.dll (include/b747_scalar_legacy.h)
 
 nvcc cross-compiles without a GPU; the .so files are git-ignored but travel with the tree.
 """
@@ -25,9 +26,11 @@ UNITS = {
     "b747_kernels_f32.cu": ["-prec-div=false", "-prec-sqrt=false"],
     "b747_capi.cu": [],
     "b747_scalar.cu": [],
+    "b747_scalar_legacy.cu": [],
 }
 HEADERS = ["b747_common.cuh", "b747_kernels.h", "b747_model_f64.cuh", "b747_model_mx.cuh", "b747_poly.h", "b747_tables.h",
-           "../../include/b747.h", "../../include/b747_params.h", "../../include/b747_scalar.h"]
+           "../../include/b747.h", "../../include/b747_params.h", "../../include/b747_scalar.h",
+           "../../include/b747_scalar_legacy.h"]
 
 
 def _nvcc():
@@ -67,6 +70,10 @@ def build_native(force=False, verbose=False):
     scal = os.path.join(LIBDIR, "model_simple.so")
     if force or _stale(scal, core + [objs["b747_scalar.cu"]]):
         subprocess.run([nvcc] + ARCH + ["-shared", "-o", scal] + core + [objs["b747_scalar.cu"]] +
+                       ["-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
+    legacy = os.path.join(LIBDIR, "model.so")
+    if force or _stale(legacy, core + [objs["b747_scalar_legacy.cu"]]):
+        subprocess.run([nvcc] + ARCH + ["-shared", "-o", legacy] + core + [objs["b747_scalar_legacy.cu"]] +
                        ["-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
     return lib, scal
 

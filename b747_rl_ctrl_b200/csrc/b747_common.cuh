@@ -53,7 +53,9 @@ enum { FL_MEM_SS = 1, FL_MEM_CS = 2, FL_USE_CTRL = 4, FL_OSC = 8 };
   X(state_x) X(state_y) X(state_Vx) X(state_Vy) X(state_vartheta) X(state_wz) X(sim_time) X(vartheta_zh) \
   X(U_com_PID) X(CXa) X(CYa) X(mz) X(K_alpha) X(dCm_ddeltaz) X(U_com) X(deltaz_RP) X(dvartheta)      \
   X(dvartheta_int) X(dvartheta_dt) X(dvartheta_dt_dt) X(TAE) X(ITAE) X(TSE) X(ITSE) X(AE) X(IAE)     \
-  X(SE) X(ISE) X(alpha) X(V) X(Mach)
+  X(SE) X(ISE) X(alpha) X(V) X(Mach)                                                                \
+  /* table outputs BEFORE the (1 + aero_err) gains: what the legacy model_win64.dll exports as CXa / CYa / mz / dCm */ \
+  X(CXa_tab) X(CYa_tab) X(mz_tab) X(dCm_tab)
 
 enum Signal {
 #define X(n) SIG_##n,

@@ -487,6 +487,7 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
       SG(dvartheta_dt_dt, dv_dt_dt); SG(TAE, fabsf(dv) * time); SG(ITAE, qn); SG(TSE, dv * dv * time);
       SG(ITSE, (float)s4.itse); SG(AE, fabsf(dv)); SG(IAE, qn); SG(SE, dv * dv); SG(ISE, qn); SG(alpha, o.alpha);
       SG(V, o.V); SG(Mach, o.Mach);
+      SG(CXa_tab, qn); SG(CYa_tab, qn); SG(mz_tab, qn); SG(dCm_tab, qn);  // float64 handles only (legacy boundary)
 #undef SG
     }
     // Outputs.  Packed form (b747_step*_packed, observation layouts of three scalars): ONE 128-bit store per env --

@@ -167,6 +167,7 @@ __device__ __forceinline__ void export_signals64(double* __restrict__ sig, size_
   SG(dvartheta_int, Xs4[IX_dvi]); SG(dvartheta_dt, o.dv_dt); SG(dvartheta_dt_dt, o.dv_dt_dt);
   SG(TAE, o.TAE); SG(ITAE, Xs4[IX_itae]); SG(TSE, o.TSE); SG(ITSE, Xs4[IX_itse]); SG(AE, o.AE);
   SG(IAE, Xs4[IX_iae]); SG(SE, o.SE); SG(ISE, Xs4[IX_ise]); SG(alpha, o.alpha); SG(V, o.V); SG(Mach, o.Mach);
+  SG(CXa_tab, o.CXa_tab); SG(CYa_tab, o.CYa_tab); SG(mz_tab, o.mz_tab); SG(dCm_tab, o.dCm_tab);
 #undef SG
 }
 

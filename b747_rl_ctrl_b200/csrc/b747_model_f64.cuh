@@ -38,6 +38,7 @@ enum { IX_x = 0, IX_h, IX_q0, IX_q3, IX_Vx, IX_Vy, IX_wz, IX_csi, IX_csf, IX_ssi
 struct Pass64 {
   double th, V, alpha, Mach, CXa, CYa, mz, K_alpha, dCm, U_com, U_com_PID, deltaz_RP, vartheta_zh;
   double dv, dv_dt, dv_dt_dt, SE, TSE, AE, TAE, td, rl_out;
+  double CXa_tab, CYa_tab, mz_tab, dCm_tab;  // table outputs before the aero-error gains (legacy signal taps)
   bool and_ss, and_cs;
 };
 
@@ -181,8 +182,10 @@ __device__ __forceinline__ void pass64(const double* __restrict__ P, const Model
   double Mach = V / asnd;
   o.Mach = Mach;
   if (major) { hd.sumA[1] = r.aerr[1] + P[51]; hd.sumA[0] = r.aerr[0] + P[51]; }
-  double CYa = look2_64<0>(Mach, ad, P + 42, P + 46, P + 22, 3, 4, 4, r.lut) * hd.sumA[1];
-  double CXa = look2_64<2>(Mach, CYa, P + 108, P + 112, P + 52, 3, 13, 4, r.lut) * hd.sumA[0];
+  o.CYa_tab = look2_64<0>(Mach, ad, P + 42, P + 46, P + 22, 3, 4, 4, r.lut);
+  double CYa = o.CYa_tab * hd.sumA[1];
+  o.CXa_tab = look2_64<2>(Mach, CYa, P + 108, P + 112, P + 52, 3, 13, 4, r.lut);
+  double CXa = o.CXa_tab * hd.sumA[0];
   o.CYa = CYa; o.CXa = CXa;
   double Tr = T * P[127];
   double pw = (Tr < 0.0 && P[128] > floor(P[128])) ? -rt_pow_64(-Tr, P[128]) : rt_pow_64(Tr, P[128]);
@@ -224,14 +227,16 @@ __device__ __forceinline__ void pass64(const double* __restrict__ P, const Model
   if (mp.use_RL >= P[148]) o.U_com = P[147] > fabs(0.0 - o.U_com_PID) ? 0.0 : o.U_com_PID;
   else o.U_com = mp.use_PID_SS >= P[9] ? o.U_com_PID : r.deltaz;
   if (major) { hd.sumA[3] = r.aerr[3] + P[216]; hd.sumA[4] = r.aerr[4] + P[216]; }
-  o.dCm = look2_64<4>(h, Mach, P + 201, P + 206, P + 151, 4, 9, 5, r.lut) * hd.sumA[3];
+  o.dCm_tab = look2_64<4>(h, Mach, P + 201, P + 206, P + 151, 4, 9, 5, r.lut);
+  o.dCm = o.dCm_tab * hd.sumA[3];
   {
     double f;
     unsigned i = prelookup64c<6>(ad, P + 225, 6, f, r.lut);
     o.K_alpha = ((P[218 + i + 1] - P[218 + i]) * f + P[218 + i]) * hd.sumA[4];
   }
   if (major) hd.sumA[2] = r.aerr[2] + P[216];
-  o.mz = look2_64<7>(Mach, ad, P + 276, P + 280, P + 232, 3, 10, 4, r.lut) * hd.sumA[2];
+  o.mz_tab = look2_64<7>(Mach, ad, P + 276, P + 280, P + 232, 3, 10, 4, r.lut);
+  o.mz = o.mz_tab * hd.sumA[2];
   double ax = (Fx * cs - sn * Fy) / mp.m0;
   double ay = (Fy * cs + Fx * sn) / mp.m0 - mp.g;
   double dze = mp.use_RP >= P[149] ? o.deltaz_RP : o.U_com;

@@ -300,6 +300,8 @@ class B747VecEnv(_VecEnvBase):
         # SB3 wants one info dict per env and step; building 10^5..10^6 dicts per step would dominate the step, so the
         # empty ones are shared between steps and only the environments that finished get a fresh dict
         self._no_infos = [{} for _ in range(self.num_envs)]
+        self._infos_list = list(self._no_infos)
+        self._infos_dirty = []
         self._items = {}
         od = self.engine.obs_dim
         self._packed = (not self.device_tensors) and dtype == E.F32 and od == 3
@@ -351,7 +353,7 @@ class B747VecEnv(_VecEnvBase):
             self.engine.step(self._act_d, self._obs_d, self._rew_d, self._done_d, self._term_d)
             self.engine.synchronize()
             done_any = bool(self._done_d.any().item())
-            infos = self._infos(self._done_d.cpu().numpy(), self._term_d) if done_any else self._no_infos
+            infos = self._infos(self._done_d.cpu().numpy(), self._term_d) if done_any else self._clean_infos()
             self._last = (self._obs_d, self._rew_d)
             return self._obs_d, self._rew_d, self._done_d.bool(), infos
         np.copyto(self._act_h, np.asarray(a).reshape(self.num_envs), casting="unsafe")
@@ -363,7 +365,7 @@ class B747VecEnv(_VecEnvBase):
             obs, rew = out[:, :3], out[:, 3]
             if self.copy_outputs:
                 obs, rew = obs.copy(), rew.copy()
-            infos = self._no_infos
+            infos = self._clean_infos()
             if done.any():
                 idx = np.flatnonzero(done)
                 infos = self._infos_idx(idx, obs[idx].copy())   # the record holds the observation BEFORE the auto-reset
@@ -372,7 +374,7 @@ class B747VecEnv(_VecEnvBase):
             return obs, rew, done, infos
         self.engine.step_host(self._act_h, self._obs, self._rew, self._done, self._term)
         done = self._done.astype(bool)
-        infos = self._infos(self._done, self._term) if done.any() else self._no_infos
+        infos = self._infos(self._done, self._term) if done.any() else self._clean_infos()
         obs, rew = self._obs.copy(), self._rew.copy()
         self._last = (obs, rew)
         return obs, rew, done, infos
@@ -381,24 +383,39 @@ class B747VecEnv(_VecEnvBase):
         self.step_async(actions)
         return self.step_wait()
 
+    def _clean_infos(self):
+        for i in self._infos_dirty:
+            self._infos_list[i] = self._no_infos[i]
+        self._infos_dirty = []
+        return self._infos_list
+
     def _infos(self, done, term):
         idx = np.nonzero(done)[0]
         if not len(idx):
-            return self._no_infos
+            return self._clean_infos()
         dev = hasattr(term, "cpu")
         rows = term[idx] if not dev else term[th_index(term, idx)]
         return self._infos_idx(idx, rows)
 
     def _infos_idx(self, idx, rows):
-        infos = list(self._no_infos)
-        ret, ln = self.engine.last_episode_of(idx) if self.monitor else (None, None)   # only the finished envs' records
-        t = round(time.time() - self._t0, 6)
+        """One info dict per env (SB3's contract) at O(finished envs) per step: the list object is reused, the entries of
+        the envs that finished in the PREVIOUS step go back to the shared empty dict, the ones that finished now get
+        {"terminal_observation", "episode"}.  (SB3 consumes `infos` within the step that returned it.)"""
+        infos = self._infos_list
+        for i in self._infos_dirty:
+            infos[i] = self._no_infos[i]
+        idx_l = idx.tolist()
         dev = hasattr(rows, "cpu")
-        for j, i in enumerate(idx):
-            info = {"terminal_observation": rows[j].clone() if dev else rows[j]}
-            if self.monitor:
-                info["episode"] = {"r": float(ret[j]), "l": int(ln[j]), "t": t}
-            infos[i] = info
+        rows_l = [r.clone() for r in rows] if dev else list(rows)
+        if self.monitor:
+            ret, ln = self.engine.last_episode_of(idx)   # only the finished envs' records
+            t = round(time.time() - self._t0, 6)
+            for i, row, r, l in zip(idx_l, rows_l, ret.tolist(), ln.tolist()):
+                infos[i] = {"terminal_observation": row, "episode": {"r": r, "l": l, "t": t}}
+        else:
+            for i, row in zip(idx_l, rows_l):
+                infos[i] = {"terminal_observation": row}
+        self._infos_dirty = idx_l
         return infos
 
     def close(self):

@@ -71,6 +71,26 @@ static void __attribute__((ms_abi)) import_trap(void) {
   abort();
 }
 
+/* The legacy model_win64.dll (MinGW) links its CRT dynamically: the numeric path reaches msvcrt for `asin` and the
+ * mem* / allocation routines (everything else -- sin, cos, atan2, pow, exp, sqrt -- is MinGW's static libmingwex inside the
+ * DLL).  These are resolved by NAME to host functions behind Microsoft-ABI thunks; every other import stays a trap. */
+#include <math.h>
+static double __attribute__((ms_abi)) t_asin(double x) { return asin(x); }
+static void *__attribute__((ms_abi)) t_memcpy(void *d, const void *s_, size_t n) { return memcpy(d, s_, n); }
+static void *__attribute__((ms_abi)) t_memset(void *d, int c, size_t n) { return memset(d, c, n); }
+static void *__attribute__((ms_abi)) t_malloc(size_t n) { return malloc(n); }
+static void *__attribute__((ms_abi)) t_calloc(size_t a, size_t b) { return calloc(a, b); }
+static void __attribute__((ms_abi)) t_free(void *p) { free(p); }
+static const struct { const char *name; void *fn; } k_thunks[] = {
+    {"asin", (void *)t_asin}, {"memcpy", (void *)t_memcpy}, {"memset", (void *)t_memset},
+    {"malloc", (void *)t_malloc}, {"calloc", (void *)t_calloc}, {"free", (void *)t_free},
+};
+static void *resolve_import(const char *name) {
+  for (size_t i = 0; i < sizeof k_thunks / sizeof k_thunks[0]; i++)
+    if (!strcmp(k_thunks[i].name, name)) return k_thunks[i].fn;
+  return (void *)import_trap;
+}
+
 static inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
 static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -128,11 +148,16 @@ static int load_image(uint8_t *img, b747ref_inst *in) {
       p += bsz;
     }
   }
-  /* import table: every IAT slot -> trap */
+  /* import table: every IAT slot -> trap, except the few msvcrt routines resolved by name (resolve_import) */
   if (imp_rva) {
     for (uint8_t *d = img + imp_rva; rd32(d + 12); d += 20) {
       uint64_t *iat = (uint64_t *)(img + rd32(d + 16));
-      for (; *iat; iat++) *iat = (uint64_t)(uintptr_t)import_trap;
+      const uint64_t *names = rd32(d) ? (const uint64_t *)(img + rd32(d)) : NULL; /* OriginalFirstThunk: hint/name RVAs */
+      for (unsigned k = 0; iat[k]; k++) {
+        void *fn = (void *)import_trap;
+        if (names && names[k] && !(names[k] >> 63) && names[k] < img_size) fn = resolve_import((const char *)img + names[k] + 2);
+        iat[k] = (uint64_t)(uintptr_t)fn;
+      }
     }
   }
   /* W^X: headers and read-only sections -> R, code -> R+X, writable data stays RW (never executable) */
