@@ -31,8 +31,14 @@ PARAMS = {
 N_BLOCK_PARAMS = 298  # doubles in model_simple_P
 
 
+def disabled() -> bool:
+    """B747_NO_DLL_ORACLE=1 switches every path that executes the reference's DLL machine code off: tests that need it
+    skip, bench.py's CPU legs fall back to the plain-C restatement (cpu_baseline.kind "port")."""
+    return os.environ.get("B747_NO_DLL_ORACLE", "") not in ("", "0")
+
+
 def available() -> bool:
-    return os.path.exists(REF_SO)
+    return os.path.exists(REF_SO) and not disabled()
 
 
 _lib = None

@@ -20,7 +20,8 @@ FUNCTIONS = ("model_initialize", "model_step", "model_terminate")
 
 
 def available():
-    return os.path.exists(LEGACY_SO)
+    from . import dllref
+    return os.path.exists(LEGACY_SO) and not dllref.disabled()
 
 
 class LegacyDll:

@@ -35,7 +35,8 @@ SHIM = os.path.join(_HERE, "_ref", "model_simple.so")
 
 
 def available():
-    return os.path.exists(os.path.join(REFERENCE, "env", "ctrl_env.py")) and os.path.exists(SHIM)
+    from . import dllref
+    return os.path.exists(os.path.join(REFERENCE, "env", "ctrl_env.py")) and os.path.exists(SHIM) and not dllref.disabled()
 
 
 class _Anything:
