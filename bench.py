@@ -466,6 +466,20 @@ def run_cuda(args, rank, local_rank, world):
             "episode_stats": summarize(stats)}
     if world == 1 and main_cfg:
         line["e2e_vecenv"] = extra_vec
+    if world == 1 and main_cfg and not args.no_cpu_baseline:
+        # BASELINE configs[4]: PPO end to end on a 65536-env GPU VecEnv (torch MLP policy, rollout + update phases replayed as
+        # CUDA graphs): env-steps/s including the updates (SB3's time/fps) and wall-clock to the reference's reward level
+        try:
+            eng.close()
+            from b747_rl_ctrl_b200 import ppo
+            r = ppo.train(n_envs=65536, threshold=225.0, max_seconds=30.0, seed=1, device=local_rank)
+            line["ppo_65536"] = {"steps_per_s": r["steps_per_s"], "seconds": r["seconds"], "steps": r["steps"],
+                                 "reached": r["reached"], "final_ep_rew_mean": r["final_ep_rew_mean"], "cuda_graphs": r["graphs"],
+                                 "hyper": r["hyper"],
+                                 "reference": "ep_rew_mean 225.7 after 98 304 steps at ~340 env-steps/s (4 SubprocVecEnv workers, "
+                                              "tensorboard.xlsx; BASELINE.md)"}
+        except Exception as e:  # never hides the headline
+            line["ppo_65536"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             _, info, _ = cpu_reference_rate(3, 1, 300000 if K == 10 else 300000, substeps=K)
