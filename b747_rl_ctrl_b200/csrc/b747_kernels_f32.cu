@@ -625,10 +625,8 @@ int f32_alloc(const DevCfg& c, StateF32& s, bool export_signals, cudaStream_t st
             cudaMalloc(&s.tables, sizeof(float4) * ft::CELLS) == cudaSuccess &&
             cudaMalloc(&s.tile_ctr, sizeof(unsigned int) * 64) == cudaSuccess &&
             cudaMemcpy(s.tables, F.v.data(), sizeof(float4) * ft::CELLS, cudaMemcpyHostToDevice) == cudaSuccess;
-  if (!ok) {  // release whatever was allocated: a retry with fewer envs must find the HBM free
-    const cudaError_t e = cudaGetLastError();
-    f32_free(s);
-    (void)e;
+  if (!ok) {  // release whatever was allocated: a retry with fewer envs must find the HBM free (the CUDA error stays
+    f32_free(s);  // readable for the caller's message)
     return -1;
   }
   cudaMemsetAsync(s.D, 0, sizeof(double2) * np * ND_GROUPS, stream);
