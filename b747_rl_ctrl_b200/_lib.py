@@ -76,6 +76,7 @@ def load():
     L.b747_step.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b747_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b747_set_host_chunks.argtypes = [vp, c_int]
+    L.b747_packed_record_floats.argtypes = [c_int]
     L.b747_step_packed.argtypes = [vp, vp, vp, vp]
     L.b747_step_host_packed.argtypes = [vp, vp, vp, vp]
     L.b747_set_host_mode.argtypes = [vp, c_int]

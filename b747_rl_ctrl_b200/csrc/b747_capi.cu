@@ -529,13 +529,16 @@ extern "C" int b747_step_host(b747_handle* h, const void* act, void* obs, void* 
 }
 
 // ---- packed outputs ------------------------------------------------------------------------------
-// One float4 per env (obs[3] before any auto-reset, reward) + one done bit per env: what the SB3-facing VecEnv needs from a
-// step, in ONE 128-bit store per thread and one ballot word per warp.  Observation layouts of three scalars only.
+// One record per env (obs before any auto-reset, reward, padded to whole float4s) + one done bit per env: what the
+// SB3-facing VecEnv needs from a step; ONE 128-bit store per thread for the 3-scalar layouts, 2-3 for the wider ones.
 static int packed_ok(b747_handle* h) {
   if (h->cfg.dtype != B747_F32) return fail(B747_ERR_STATE, "packed outputs need an f32 handle");
-  if (h->dc.obs_dim != 3) return fail(B747_ERR_STATE, "packed outputs need a 3-scalar observation layout (PID_LIKE)");
   if (!h->cfg.env_layer) return fail(B747_ERR_STATE, "handle was created with env_layer=0; use b747_model_step");
   return B747_OK;
+}
+extern "C" int b747_packed_record_floats(int obs_type) {
+  const int od = obs_dim_of(obs_type);
+  return od < 0 ? -1 : 4 * ((od + 4) / 4);
 }
 
 extern "C" int b747_step_packed(b747_handle* h, const float* act_dev, float* out4_dev, uint32_t* done_bits_dev) {
@@ -570,6 +573,7 @@ extern "C" int b747_step_host_packed(b747_handle* h, const float* act, float* ou
   if (prc) return prc;
   CU(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)h->cfg.n_envs, np = (size_t)h->dc.n_pad, nw = (n + 31) / 32;
+  const size_t rec4 = ((size_t)h->dc.obs_dim + 4) / 4;  // float4s per record
   if (!h->d_bits) CU(cudaMalloc(&h->d_bits, sizeof(uint32_t) * (np / 32)));
   float* m_act = (float*)mapped_ptr(act);
   float4* m_out = (float4*)mapped_ptr(out4);
@@ -614,7 +618,7 @@ extern "C" int b747_step_host_packed(b747_handle* h, const float* act, float* ou
   }
   // copy mode (pageable buffers, or asked for): H2D, step into device staging, D2H -- chunked like b747_step_host when
   // the buffers are pinned
-  if (!h->d_out4) CU(cudaMalloc(&h->d_out4, sizeof(float4) * np));
+  if (!h->d_out4) CU(cudaMalloc(&h->d_out4, sizeof(float4) * rec4 * np));
   const bool pinned = is_pinned(act) && is_pinned(out4) && is_pinned(done_bits);
   int chunks = (pinned && n >= ((size_t)1 << 17)) ? (h->host_chunks ? h->host_chunks : 4) : 1;
   const size_t per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
@@ -650,7 +654,7 @@ extern "C" int b747_step_host_packed(b747_handle* h, const float* act, float* ou
       CU(cudaGetLastError());
       CU(cudaEventRecord(h->ev_k[c], sc));
       CU(cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
-      CU(cudaMemcpyAsync(out4 + 4 * lo, h->d_out4 + lo, sizeof(float4) * m, cudaMemcpyDeviceToHost, h->s_out));
+      CU(cudaMemcpyAsync(out4 + 4 * rec4 * lo, h->d_out4 + rec4 * lo, sizeof(float4) * rec4 * m, cudaMemcpyDeviceToHost, h->s_out));
       CU(cudaMemcpyAsync(done_bits + lo / 32, h->d_bits + lo / 32, sizeof(uint32_t) * ((m + 31) / 32), cudaMemcpyDeviceToHost, h->s_out));
     }
     CU(cudaEventRecord(h->ev_done, h->s_out));
@@ -662,7 +666,7 @@ extern "C" int b747_step_host_packed(b747_handle* h, const float* act, float* ou
   launch_env_step32(h->dc, h->s32, (const float*)h->d_act, nullptr, nullptr, nullptr, nullptr, h->stream, h->d_out4, h->d_bits);
   h->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out4, h->d_out4, sizeof(float4) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(out4, h->d_out4, sizeof(float4) * rec4 * n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(done_bits, h->d_bits, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return B747_OK;

@@ -490,12 +490,22 @@ __global__ void B747_STEP_BOUNDS k_env_step32(DevCfg c, MP32 mp, StateF32 st, co
       SG(CXa_tab, qn); SG(CYa_tab, qn); SG(mz_tab, qn); SG(dCm_tab, qn);  // float64 handles only (legacy boundary)
 #undef SG
     }
-    // Outputs.  Packed form (b747_step*_packed, observation layouts of three scalars): ONE 128-bit store per env --
-    // (obs before any auto-reset, reward) -- and the done flags as one ballot word per warp (below); the observation after
-    // an auto-reset is all zeros (ControllerEnv.reset), so the caller derives it from the done bit.
+    // Outputs.  Packed form (b747_step*_packed): one record of 4 * ceil((obs_dim + 1) / 4) floats per env --
+    // (obs before any auto-reset, reward, zero padding), a single 128-bit store for the 3-scalar layouts -- and the done
+    // flags as one ballot word per warp (below); the observation after an auto-reset is all zeros (ControllerEnv.reset), so
+    // the caller derives it from the done bit.
     const bool packed = out4 != nullptr;
     if (packed) {
-      out4[i] = make_float4(obs[0], obs[1], obs[2], rew);
+      if (!GEN) {
+        out4[i] = make_float4(obs[0], obs[1], obs[2], rew);
+      } else {
+        const int rec4 = (od + 4) >> 2;  // float4s per record
+        float rec[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) rec[k] = k < od ? obs[k < 10 ? k : 9] : (k == od ? rew : 0.f);
+        float4* q = out4 + (size_t)i * rec4;
+        for (int k = 0; k < rec4; k++) q[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+      }
     } else {
       rew_out[i] = rew;
       done_out[i] = done ? 1 : 0;

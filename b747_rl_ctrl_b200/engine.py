@@ -162,13 +162,18 @@ class BatchEngine:
             return obs, rew, done, terminal_obs
         return obs, rew, done
 
+    @property
+    def record_floats(self):
+        """Floats per packed record: 4 * ceil((obs_dim + 1) / 4) -- obs, reward, zero padding."""
+        return int(self._L.b747_packed_record_floats(self.cfg.obs_type))
+
     def step_packed(self, actions, out4, done_bits):
-        """Device tensors: out4 [n_envs, 4] float32 = (obs before auto-reset, reward), done_bits [(n_envs+31)//32]
-        int32/uint32 (one bit per env).  f32 handles with a 3-scalar observation layout.  Asynchronous."""
+        """Device tensors: out4 [n_envs, record_floats] float32 = (obs before auto-reset, reward, padding), done_bits
+        [(n_envs+31)//32] int32/uint32 (one bit per env).  f32 handles.  Asynchronous."""
         check(self._L.b747_step_packed(self._h, _ptr(actions), _ptr(out4), _ptr(done_bits)))
 
     def step_host_packed(self, actions, out4, done_bits):
-        """Host buffers (float32 [n_envs], float32 [n_envs, 4], uint32 [(n_envs+31)//32]); page-locked buffers are read
+        """Host buffers (float32 [n_envs], float32 [n_envs, record_floats], uint32 [(n_envs+31)//32]); page-locked buffers are read
         and written by the kernel directly (zero-copy).  Synchronised on return."""
         check(self._L.b747_step_host_packed(self._h, _ptr(actions), _ptr(out4), _ptr(done_bits)))
 

@@ -12,9 +12,9 @@ calls the reference makes on its vectorised env -- `env.get_attr('ctrl')[0].stor
 environment 0's (the reference's callbacks hold a single env and read `env.ctrl`, neural/callbacks.py:61-64).
 
 Two I/O modes:
-  * numpy (default; what SB3 passes): pinned host buffers.  The canonical 3-scalar observation layout in f32 mode takes
-    the packed zero-copy path (b747_step_host_packed: the kernel reads the actions from and stores one float4 record
-    per env into the pinned buffers, done flags come back as one bit per env); other layouts go through b747_step_host;
+  * numpy (default; what SB3 passes): pinned host buffers.  f32 handles take the packed zero-copy path
+    (b747_step_host_packed: the kernel reads the actions from and stores one (obs, reward) record per env into the pinned
+    buffers, done flags come back as one bit per env); float64 handles go through b747_step_host;
   * torch device tensors (`device_tensors=True`): obs/rew/done stay in HBM, for GPU-resident policies.
 
 When stable-baselines3 is importable the class derives from its `VecEnv`, so `PPO('MlpPolicy', env)` takes it as is
@@ -304,14 +304,14 @@ class B747VecEnv(_VecEnvBase):
         self._infos_dirty = []
         self._items = {}
         od = self.engine.obs_dim
-        self._packed = (not self.device_tensors) and dtype == E.F32 and od == 3
+        self._packed = (not self.device_tensors) and dtype == E.F32
         self._last = None  # (obs, rew) arrays of the last step
         self._keep = []
         if self.device_tensors:
             self._act_d, self._obs_d, self._rew_d, self._done_d, self._term_d = self.engine.alloc_io(terminal_obs=True)
         elif self._packed:
             self._act_h = self._pin((self.num_envs,), np.float32)
-            self._out4 = [self._pin((self.num_envs, 4), np.float32) for _ in range(2)]
+            self._out4 = [self._pin((self.num_envs, self.engine.record_floats), np.float32) for _ in range(2)]
             self._bits = self._pin(((self.num_envs + 31) // 32,), np.int32)  # one done bit per env
             self._flip = 0
         else:
@@ -362,7 +362,8 @@ class B747VecEnv(_VecEnvBase):
             self._flip ^= 1
             self.engine.step_host_packed(self._act_h, out, self._bits)
             done = np.unpackbits(self._bits.view(np.uint8), bitorder="little")[:self.num_envs].view(bool)
-            obs, rew = out[:, :3], out[:, 3]
+            od = self.engine.obs_dim
+            obs, rew = out[:, :od], out[:, od]
             if self.copy_outputs:
                 obs, rew = obs.copy(), rew.copy()
             infos = self._clean_infos()

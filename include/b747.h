@@ -124,16 +124,19 @@ int b747_step_host(b747_handle *h, const void *actions, void *obs, void *rew, ui
 /* Number of chunks of b747_step_host's pipeline: 0 = automatic (4 from 128 Ki envs, else 1), 1 = no pipeline. */
 int b747_set_host_chunks(b747_handle *h, int n_chunks);
 
-/* Packed outputs (f32 handles, observation layouts of three scalars = ObservationType.PID_LIKE): per env ONE record
- *   out4[i] = { obs[0], obs[1], obs[2], reward }   -- the observation BEFORE any auto-reset, i.e. SB3's
- *                                                    infos[i]["terminal_observation"] where the env finished;
+/* Packed outputs (f32 handles): per env ONE record of R = b747_packed_record_floats(obs_type) = 4 * ceil((obs_dim + 1) / 4)
+ * floats (4 for PID_LIKE, 8 for SPEED_MODE and MODEL_STATE, 12 for PID_AERO and PID_SPEED_AERO):
+ *   out[i * R + k]       = obs[k], k < obs_dim  -- the observation BEFORE any auto-reset, i.e. SB3's
+ *                                                  infos[i]["terminal_observation"] where the env finished;
+ *   out[i * R + obs_dim] = reward; the rest of the record is zero padding;
  *   bit (i & 31) of done_bits[i >> 5] = done flag  -- done_bits holds (n_envs + 31) / 32 words.
  * The observation after an auto-reset is all zeros (every exported signal is zero after Model.initialize,
- * env/ctrl_env.py:273-278), so a caller derives the returned observation as done ? 0 : out4[i].obs.
+ * env/ctrl_env.py:273-278), so a caller derives the returned observation as done ? 0 : record.obs.
  * b747_step_packed: device buffers, asynchronous on the handle's stream.
  * b747_step_host_packed: HOST buffers, synchronised on return.  With page-locked (cudaHostAlloc / cudaHostRegister)
  * buffers the kernel reads the actions from and stores the records into the caller's memory directly (posted PCIe
- * writes of 512 contiguous bytes per warp that overlap the stepping of the other envs); pageable buffers are staged. */
+ * writes of whole 128-bit words that overlap the stepping of the other envs); pageable buffers are staged. */
+int b747_packed_record_floats(int obs_type);
 int b747_step_packed(b747_handle *h, const float *actions_dev, float *out4_dev, uint32_t *done_bits_dev);
 int b747_step_host_packed(b747_handle *h, const float *actions, float *out4, uint32_t *done_bits);
 /* Host path of b747_step_host_packed with page-locked buffers: 0 staged copies (chunk pipeline), 1 actions copied /

@@ -213,12 +213,34 @@ def test_packed_host_step_equals_plain_step(n, mode):
     ref.close(); pk.close()
 
 
+@pytest.mark.parametrize("obs_type,od,R", [(1, 5, 8), (4, 7, 8), (2, 8, 12), (3, 10, 12)])
+def test_packed_records_of_wider_observation_layouts(obs_type, od, R):
+    """Records are 4 * ceil((obs_dim + 1) / 4) floats: observation, reward, zero padding -- for every layout."""
+    import torch
+    from b747_rl_ctrl_b200 import engine as E
+    n = 1500
+    kw = dict(dtype=E.F32, seed=6, sample_time=0.05, tk=0.35, obs_type=obs_type)
+    ref, pk = E.BatchEngine(n_envs=n, **kw), E.BatchEngine(n_envs=n, **kw)
+    assert pk.record_floats == R and pk.obs_dim == od
+    ref.reset(); pk.reset()
+    keep = [torch.zeros(n).pin_memory(), torch.zeros(n, R).pin_memory(), torch.zeros((n + 31) // 32, dtype=torch.int32).pin_memory()]
+    act, out, bits = keep[0].numpy(), keep[1].numpy(), keep[2].numpy().view(np.uint32)
+    rng = np.random.default_rng(2)
+    term = np.zeros((n, od), np.float32)
+    for k in range(9):
+        a = rng.uniform(-1, 1, n).astype(np.float32)
+        _, rew, done, term = ref.step_host(a, terminal_obs=term)
+        act[:] = a
+        out[:] = -7.0
+        pk.step_host_packed(act, out, bits)
+        assert np.array_equal(np.unpackbits(bits.view(np.uint8), bitorder="little")[:n], done), k
+        assert np.array_equal(out[:, :od], term) and np.array_equal(out[:, od], rew) and (out[:, od + 1:] == 0).all(), k
+    assert done.sum() == 0 and ref.episode_stats()[0] == n
+    ref.close(); pk.close()
+
+
 def test_packed_step_rejected_where_it_does_not_apply():
     from b747_rl_ctrl_b200 import engine as E
-    e = E.BatchEngine(n_envs=64, dtype=E.F32, obs_type=E.OBS_SPEED_MODE)
-    with pytest.raises(E.B747Error):
-        e.step_host_packed(np.zeros(64, np.float32), np.zeros((64, 4), np.float32), np.zeros(2, np.uint32))
-    e.close()
     e = E.BatchEngine(n_envs=64, dtype=E.F64)
     with pytest.raises(E.B747Error):
         e.step_host_packed(np.zeros(64, np.float32), np.zeros((64, 4), np.float32), np.zeros(2, np.uint32))
