@@ -25,10 +25,17 @@ ids = torch.arange(n, device="cuda")
 for t in range(ep_len):
     eng.step(pool[t % 8], obs, rew, done)
     eng.reset(mask=((ids % ep_len) == t).to(torch.uint8))
+import os
+packed = os.environ.get("B747_PACKED", "0") != "0"
+out4 = torch.empty(n, eng.record_floats, device="cuda")
+bits = torch.empty((n + 31) // 32, dtype=torch.int32, device="cuda")
+for k in range(5):
+    eng.step_packed(pool[k % 8], out4, bits) if packed else eng.step(pool[k % 8], obs, rew, done)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for k in range(steps):
-    eng.step(pool[k % 8], obs, rew, done)
+    eng.step_packed(pool[k % 8], out4, bits) if packed else eng.step(pool[k % 8], obs, rew, done)
 e1.record()
 torch.cuda.synchronize()
-print(f"K={K} steady state: {e0.elapsed_time(e1) / steps:.4f} ms/step, episodes {eng.episode_stats()[0]:.0f}")
+print(f"K={K} steady state{' (packed outputs)' if packed else ''}: {e0.elapsed_time(e1) / steps:.4f} ms/step, "
+      f"episodes {eng.episode_stats()[0]:.0f}")
