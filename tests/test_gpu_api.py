@@ -394,6 +394,20 @@ def test_vec_env_device_tensors():
         obs, rew, dones, infos = venv.step(a)
     assert obs.is_cuda and rew.is_cuda and dones.dtype == torch.bool and float(rew.min()) > 0
     venv.close()
+    # episodes finishing on the device path: terminal observations are device tensors, monitor records host floats
+    venv = B747VecEnv(256, device_tensors=True, tk=0.5, sample_time=0.05, seed=2)
+    venv.reset()
+    a = torch.zeros(256, 1, device="cuda")
+    for k in range(12):
+        last = venv._obs_d.clone()
+        obs, rew, dones, infos = venv.step(a)
+        if k == 9:
+            assert bool(dones.all()) and float(obs.abs().max()) == 0.0
+            assert all(i["terminal_observation"].is_cuda and i["episode"]["l"] == 10 and i["episode"]["r"] > 0 for i in infos)
+            assert float(infos[7]["terminal_observation"].abs().max()) > 0
+        else:
+            assert not bool(dones.any()) and infos[7] == {}
+    venv.close()
 
 
 def test_reset_mask_and_reset_to():
