@@ -44,7 +44,7 @@ def run_control_test(policy=None, vartheta_ref=DEFAULT_REFS, state0=DEFAULT_STAT
     K = E._lib.substeps_of(sample_time)
     n_model = E._lib.done_tick_of(tk)
     eng = E.BatchEngine(n_envs=n, dtype=dtype, device=device, obs_type=_enum(observation_type), rew_type=_enum(reward_type),
-                        norm_obs=norm_obs, norm_act=norm_act, ctrl_type=_enum(ctrl_type), ctrl_mode=_enum(ctrl_mode, 0),
+                        norm_obs=norm_obs, norm_act=norm_act, ctrl_type=_enum(ctrl_type), ctrl_mode=_enum(ctrl_mode, E.MODE_NONE),
                         reset_ref_mode=E.RESET_NONE, disturbance_mode=_enum(disturbance_mode, E.DIST_NONE),
                         use_limiter=use_limiter, tk=tk, sample_time=sample_time, action_max=action_max,
                         vartheta_max=vartheta_max, aero_err=aero_err, reward_config=reward_config, auto_reset=False,
@@ -147,7 +147,7 @@ def run_agent_test(ref_values, policies=None, state0=DEFAULT_STATE0, *, ctrl_typ
     pid_kw = {k: v for k, v in env_kwargs.items() if k not in ("ctrl_mode", "sample_time", "observation_type", "reward_type")}
     for i, coefs in enumerate(coef_sets):
         name = base_name + (f" [{i + 1}]" if len(coef_sets) > 1 else "")
-        kw = dict(pid_kw, ctrl_type=pid_type, ctrl_mode=E.MODE_DIRECT, sample_time=None)
+        kw = dict(pid_kw, ctrl_type=pid_type, ctrl_mode=None, sample_time=None)   # agent.py:301: env_PID.ctrl.ctrl_mode = None
         if coefs is not None:
             kw["pid_cs" if use_ctrl else "pid_ss"] = coefs
         devices.append((name, run_control_test(None, state0=state0, **which, **kw)))

@@ -96,7 +96,7 @@ class Controller:
             obs_type=env.get("obs_type", E.OBS_PID_LIKE), rew_type=env.get("rew_type", E.REW_CLASSIC),
             norm_obs=env.get("norm_obs", True), norm_act=False,  # ControllerEnv scales the action itself, in place
             reward_config=env.get("reward_config"),
-            ctrl_type=ctrl_type.value, ctrl_mode=(ctrl_mode.value if ctrl_mode is not None else 0),
+            ctrl_type=ctrl_type.value, ctrl_mode=(ctrl_mode.value if ctrl_mode is not None else E.MODE_NONE),
             reset_ref_mode=(reset_ref_mode.value if reset_ref_mode is not None else E.RESET_NONE),
             disturbance_mode=(disturbance_mode.value if disturbance_mode is not None else E.DIST_NONE),
             use_limiter=use_limiter, tk=tk, sample_time=sample_time, action_max=action_max, vartheta_max=vartheta_max,

@@ -179,7 +179,11 @@ extern "C" int b747_create(const b747_cfg* cfg, b747_handle** out) {
   if (obs_dim_of(cfg->obs_type) < 0) return fail(B747_ERR_ARG, "unknown obs_type");
   if (cfg->rew_type < 0 || cfg->rew_type > 4) return fail(B747_ERR_ARG, "unknown rew_type");
   if (cfg->ctrl_type < 0 || cfg->ctrl_type > 3) return fail(B747_ERR_ARG, "unknown ctrl_type");
-  if (cfg->ctrl_mode < 0 || cfg->ctrl_mode > 3) return fail(B747_ERR_ARG, "unknown ctrl_mode");
+  if (cfg->ctrl_mode < B747_MODE_NONE || cfg->ctrl_mode > 3) return fail(B747_ERR_ARG, "unknown ctrl_mode");
+  // the reference asserts this in Controller.__init__ (core/controller.py:103)
+  if (cfg->ctrl_mode == B747_MODE_NONE && cfg->env_layer &&
+      (cfg->ctrl_type == B747_CTRL_MANUAL || cfg->ctrl_type == B747_CTRL_SEMI_MANUAL))
+    return fail(B747_ERR_ARG, "ctrl_mode None needs the СС PID in the loop (CtrlType.AUTO / FULL_AUTO)");
   if (cfg->reset_ref_mode < -1 || cfg->reset_ref_mode > 2) return fail(B747_ERR_ARG, "unknown reset_ref_mode");
   if (cfg->substeps < 1) return fail(B747_ERR_ARG, "substeps must be >= 1");
   if (cfg->dtype == B747_F32 && !cfg->env_layer)

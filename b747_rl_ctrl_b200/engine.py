@@ -14,6 +14,7 @@ from ._lib import F32, F64, B747Error, Cfg, Episode, check
 # enum values == the reference's (core/controller.py:14-36, env/ctrl_env.py:16-30)
 CTRL_FULL_AUTO, CTRL_AUTO, CTRL_SEMI_MANUAL, CTRL_MANUAL = 0, 1, 2, 3
 MODE_DIRECT, MODE_ADD_PROC, MODE_ANG_VEL, MODE_ADD_DIRECT = 0, 1, 2, 3
+MODE_NONE = -1  # ctrl_mode=None (CtrlType.AUTO / FULL_AUTO): action law as DIRECT, no rf reward term
 RESET_NONE, RESET_CONST, RESET_OSCILLATING, RESET_HYBRID = -1, 0, 1, 2
 DIST_NONE, DIST_AERO = -1, 0
 OBS_PID_LIKE, OBS_SPEED_MODE, OBS_PID_AERO, OBS_PID_SPEED_AERO, OBS_MODEL_STATE = 0, 1, 2, 3, 4

@@ -277,7 +277,7 @@ class B747VecEnv(_VecEnvBase):
         self.reset_ref_mode, self.disturbance_mode, self.use_limiter = reset_ref_mode, disturbance_mode, use_limiter
         self.engine = E.BatchEngine(
             n_envs=num_envs, dtype=dtype, device=device, obs_type=_val(observation_type), rew_type=_val(reward_type),
-            norm_obs=norm_obs, norm_act=norm_act, ctrl_type=_val(ctrl_type), ctrl_mode=_val(ctrl_mode, 0),
+            norm_obs=norm_obs, norm_act=norm_act, ctrl_type=_val(ctrl_type), ctrl_mode=_val(ctrl_mode, E.MODE_NONE),
             reset_ref_mode=_val(reset_ref_mode), disturbance_mode=_val(disturbance_mode, E.DIST_NONE),
             use_limiter=use_limiter, tk=tk, sample_time=sample_time, action_max=action_max, vartheta_max=vartheta_max,
             aero_err=aero_err, reward_config=reward_config, seed=seed, auto_reset=True, env_layer=True,

@@ -43,6 +43,11 @@ enum { B747_F64 = 0, B747_F32 = 1 };
 /* Enum values equal the reference's Enum values. */
 enum { B747_CTRL_FULL_AUTO = 0, B747_CTRL_AUTO = 1, B747_CTRL_SEMI_MANUAL = 2, B747_CTRL_MANUAL = 3 }; /* core/controller.py:14-19 */
 enum { B747_MODE_DIRECT = 0, B747_MODE_ADD_PROC = 1, B747_MODE_ANG_VEL = 2, B747_MODE_ADD_DIRECT = 3 }; /* core/controller.py:21-26 */
+/* ctrl_mode=None of the reference (allowed with CtrlType.AUTO / FULL_AUTO, core/controller.py:103; what ControllerAgent.test
+ * sets on its PID env, neural/agent.py:301): the action law falls through to deltaz = action like DIRECT_CONTROL
+ * (core/controller.py:241), but the CLASSIC reward's shaping term rf is 0 because the mode is not DIRECT_CONTROL
+ * (env/ctrl_env.py:141). */
+enum { B747_MODE_NONE = -1 };
 enum { B747_RESET_NONE = -1, B747_RESET_CONST = 0, B747_RESET_OSCILLATING = 1, B747_RESET_HYBRID = 2 }; /* core/controller.py:28-32 */
 enum { B747_DIST_NONE = -1, B747_DIST_AERO = 0 };                                                    /* core/controller.py:34-36 */
 enum { B747_OBS_PID_LIKE = 0, B747_OBS_SPEED_MODE = 1, B747_OBS_PID_AERO = 2, B747_OBS_PID_SPEED_AERO = 3, B747_OBS_MODEL_STATE = 4 }; /* env/ctrl_env.py:16-22 */

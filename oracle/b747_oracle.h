@@ -81,6 +81,7 @@ void b747o_iface_from_model(b747o_iface *f, b747o_model *m);
  * (core/controller.py:14-36, env/ctrl_env.py:16-30). */
 enum { B747_CTRL_FULL_AUTO = 0, B747_CTRL_AUTO = 1, B747_CTRL_SEMI_MANUAL = 2, B747_CTRL_MANUAL = 3 };
 enum { B747_MODE_DIRECT = 0, B747_MODE_ADD_PROC = 1, B747_MODE_ANG_VEL = 2, B747_MODE_ADD_DIRECT = 3 };
+enum { B747_MODE_NONE = -1 }; /* ctrl_mode=None: action law as DIRECT (core/controller.py:241), no rf reward term (env/ctrl_env.py:141) */
 enum { B747_RESET_NONE = -1, B747_RESET_CONST = 0, B747_RESET_OSCILLATING = 1, B747_RESET_HYBRID = 2 };
 enum { B747_DIST_NONE = -1, B747_DIST_AERO = 0 };
 enum { B747_OBS_PID_LIKE = 0, B747_OBS_SPEED_MODE = 1, B747_OBS_PID_AERO = 2, B747_OBS_PID_SPEED_AERO = 3, B747_OBS_MODEL_STATE = 4 };

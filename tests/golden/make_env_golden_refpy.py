@@ -40,7 +40,20 @@ FAMILIES = {
     "minimal": dict(rew_type=3),
     "tfref_unnormalised": dict(rew_type=4, norm_obs=False, norm_act=False),
     "fixed_aero_err": dict(disturbance_mode=0, aero_err=[-0.1, 0.1, -0.1, -0.1, 0.1]),
+    # explicit episodes (Controller.reset(state0) with a constant reference function, reset_ref_mode None), the СС PID in
+    # the loop and ctrl_mode None: the env ControllerAgent.test builds for its PID baseline (neural/agent.py:298-307)
+    "auto_none_explicit": dict(ctrl_type=1, ctrl_mode=-1, reset_ref_mode=-1, tk=4.0),
+    "fullauto_none_explicit": dict(ctrl_type=0, ctrl_mode=-1, reset_ref_mode=-1, tk=4.0, rew_type=2),
+    "manual_explicit_addproc": dict(ctrl_mode=1, action_max=1.0, reset_ref_mode=-1, tk=4.0),
 }
+
+
+def explicit_episode(name, e):
+    """(state0, vref, href) of env e of an explicit-episode family."""
+    s0 = [0.0, 9000.0 + 500.0 * e, 230.0 + 5.0 * e, float(e - 1), 0.0, 0.0]
+    vref = (3.0 + e) * DEG * (-1.0) ** e
+    href = s0[1] + 300.0 * (-1.0) ** e
+    return s0, vref, href
 DEFAULTS = dict(obs_type=0, rew_type=0, ctrl_type=3, ctrl_mode=0, reset_ref_mode=0, disturbance_mode=-1, norm_obs=True,
                 norm_act=True, use_limiter=False, tk=20.0, sample_time=0.05, action_max=17 * DEG, vartheta_max=10 * DEG,
                 aero_err=None)
@@ -52,7 +65,8 @@ def make_ref_env(ref, kw, rng):
     refpy.patch_rng(ref, rng)
     env = CE.ControllerEnv(
         CE.ObservationType(k["obs_type"]), CE.RewardType(k["rew_type"]), k["norm_obs"], k["norm_act"],
-        C.CtrlType(k["ctrl_type"]), C.CtrlMode(k["ctrl_mode"]),
+        C.CtrlType(k["ctrl_type"]), None if k["ctrl_mode"] < 0 else C.CtrlMode(k["ctrl_mode"]),
+        vartheta_func=k.get("vartheta_func"), h_func=k.get("h_func"),
         reset_ref_mode=None if k["reset_ref_mode"] < 0 else C.ResetRefMode(k["reset_ref_mode"]),
         disturbance_mode=None if k["disturbance_mode"] < 0 else C.DisturbanceMode(k["disturbance_mode"]),
         tk=k["tk"], sample_time=k["sample_time"], action_max=k["action_max"], vartheta_max=k["vartheta_max"],
@@ -92,7 +106,13 @@ def main():
             rng = refpy.PhiloxRandom(SEED, e)
             rng.episode = -1
             state["rng"], state["rows"] = rng, []
-            env = make_ref_env(ref, kw, rng)       # __init__ resets once: episode 0
+            if kw.get("reset_ref_mode", 0) < 0:    # explicit episode: constant reference functions + reset(state0)
+                s0, vref, href = explicit_episode(name, e)
+                env = make_ref_env(ref, dict(kw, vartheta_func=lambda _, v=vref: v, h_func=lambda _, h=href: h), rng)
+                state["rows"] = []
+                env.reset(np.array(s0))
+            else:
+                env = make_ref_env(ref, kw, rng)   # __init__ resets once: episode 0
             od = env.observation_space.shape[0]
             if obs is None:
                 obs, rew, done = np.zeros((n, steps, od)), np.zeros((n, steps)), np.zeros((n, steps), np.uint8)

@@ -31,6 +31,17 @@ def _cfg(O, m):
     return O.make_cfg(seed=m["seed"], **m["kw"])
 
 
+def _explicit(m):
+    """Families rolled from explicit episodes (Controller.reset(state0) + constant reference function)."""
+    return m["kw"].get("reset_ref_mode", 0) == -1
+
+
+def _episodes(mod, g, name, m):
+    """The explicit episodes of a family as `mod.episode(...)` descriptors (mod = oracle or engine)."""
+    rows = g[name + "/episodes"][:, 0]
+    return [mod.episode(r[:6], vref=r[7], h_ref=r[8], use_ctrl=bool(r[6]), aero_err=r[16:21]) for r in rows]
+
+
 def test_provenance_says_reference_python():
     _, meta = _golden()
     assert "/root/reference/env/ctrl_env.py" in meta["provenance"] and "unmodified" in meta["provenance"]
@@ -43,6 +54,8 @@ def test_reset_draws_match_reference_reset_code(oracle):
     g, meta = _golden()
     n_checked = 0
     for name, m in meta["families"].items():
+        if _explicit(m):
+            continue
         cfg = _cfg(oracle, m)
         eps = g[name + "/episodes"]          # [n, E, 21]
         for e in range(m["n"]):
@@ -61,6 +74,8 @@ def test_reset_draws_match_reference_reset_code(oracle):
                 assert list(ep.aero_err) == list(row[16:21]), (name, e, k)
                 n_checked += 1
     assert n_checked >= 100
+    assert {n for n, m in meta["families"].items() if _explicit(m)} == {"auto_none_explicit", "fullauto_none_explicit",
+                                                                        "manual_explicit_addproc"}
 
 
 def test_c_env_layer_over_dll_is_bit_identical_to_reference_python(oracle, dllref):
@@ -69,7 +84,7 @@ def test_c_env_layer_over_dll_is_bit_identical_to_reference_python(oracle, dllre
         cfg = _cfg(oracle, m)
         for e in range(m["n"]):
             env = oracle.RefEnv(cfg, env_id=e)
-            assert (env.reset() == 0).all()
+            assert ((env.reset_to(_episodes(oracle, g, name, m)[e]) if _explicit(m) else env.reset()) == 0).all()
             obs, rew, done = env.rollout(g[name + "/actions"][e], auto_reset=True)
             assert np.array_equal(done, g[name + "/done"][e].astype(bool)), (name, e)
             assert np.array_equal(obs, g[name + "/obs"][e]), (name, e, np.abs(obs - g[name + "/obs"][e]).max())
@@ -90,7 +105,7 @@ def test_restatement_tracks_reference_python(oracle):
     g, meta = _golden()
     for name, m in meta["families"].items():
         ob = oracle.OracleBatch(_cfg(oracle, m), m["n"])
-        ob.reset()
+        ob.reset_to(_episodes(oracle, g, name, m)) if _explicit(m) else ob.reset()
 
         def step(a):
             _, r, d, t = ob.step(a)
@@ -106,7 +121,7 @@ def test_f64_kernel_tracks_reference_python():
     g, meta = _golden()
     for name, m in meta["families"].items():
         eng = E.BatchEngine(n_envs=m["n"], dtype=E.F64, seed=m["seed"], auto_reset=True, **m["kw"])
-        eng.reset()
+        eng.reset_to(_episodes(E, g, name, m)) if _explicit(m) else eng.reset()
         term = np.zeros((m["n"], eng.obs_dim))
 
         def step(a):
@@ -128,7 +143,7 @@ def test_f32_kernel_tracks_reference_python():
     for name, m in meta["families"].items():
         ob, rb, _ = FAMILY_BOUNDS.get(name, (1e-6, 2e-3, 0.0))
         eng = E.BatchEngine(n_envs=m["n"], dtype=E.F32, seed=m["seed"], auto_reset=True, **m["kw"])
-        eng.reset()
+        eng.reset_to(_episodes(E, g, name, m)) if _explicit(m) else eng.reset()
         term = np.zeros((m["n"], eng.obs_dim), np.float32)
         acts = g[name + "/actions"]
         for k in range(m["steps"]):
