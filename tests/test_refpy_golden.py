@@ -153,3 +153,37 @@ def test_f32_kernel_tracks_reference_python():
             assert (np.abs(term - ref) <= ob * (1 + np.abs(ref))).all(), (name, k, np.abs(term - ref).max())
             assert np.abs(r - g[name + "/rew"][:, k]).max() <= rb + 0.08, (name, k)
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["manual_explicit_addproc", "auto_none_explicit", "fullauto_none_explicit"])
+def test_gym_facade_replays_reference_python(name):
+    """The single-env ControllerEnv / Controller facade (gym 0.19 API) driven exactly like the reference's env in the
+    golden generator -- constructor with constant reference functions, reset(state0), step, reset() on done -- returns the
+    reference's observations, rewards and done flags."""
+    from b747_rl_ctrl_b200.core.controller import CtrlMode, CtrlType
+    from b747_rl_ctrl_b200.env.ctrl_env import ControllerEnv, ObservationType, RewardType
+    g, meta = _golden()
+    m = meta["families"][name]
+    kw = m["kw"]
+    for e in range(2):
+        row = g[name + "/episodes"][e, 0]
+        env = ControllerEnv(ObservationType(kw.get("obs_type", 0)), RewardType(kw.get("rew_type", 0)), True, True,
+                            CtrlType(kw.get("ctrl_type", 3)), None if kw.get("ctrl_mode", 0) < 0 else CtrlMode(kw["ctrl_mode"]),
+                            vartheta_func=lambda _, v=row[7]: v, h_func=lambda _, h=row[8]: h, reset_ref_mode=None,
+                            tk=kw.get("tk", 20.0), sample_time=0.05, action_max=kw.get("action_max", 17 * np.pi / 180))
+        obs = env.reset(np.array(row[:6]))
+        assert (obs == 0).all()
+        n_done = 0
+        for k in range(200):
+            a = np.array([g[name + "/actions"][e, k]])
+            obs, r, done, info = env.step(a)
+            ref = g[name + "/obs"][e, k]
+            assert done == bool(g[name + "/done"][e, k]) and info == {}, (name, e, k)
+            assert np.allclose(obs, ref, rtol=1e-9, atol=1e-12), (name, e, k, np.abs(obs - ref).max())
+            assert abs(r - g[name + "/rew"][e, k]) <= 1e-9, (name, e, k)
+            if done:
+                n_done += 1
+                env.reset()
+        assert n_done == 2
+        env.close()
