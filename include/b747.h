@@ -171,6 +171,11 @@ const char *b747_field_name(int field);
 int b747_field_index(const char *name);
 int b747_get_field(b747_handle *h, int field, double *out_host);
 int b747_set_field(b747_handle *h, int field, const double *in_host);
+/* f32 handles integrate only what their configuration's kernel tier needs: "x", "cs_int", "cs_flt" (canonical and
+ * general tiers without the altitude loop) and "sig_vzh" (canonical tier) keep their reset values there.  Writing
+ * "flags" (closing the altitude loop of single envs by hand) moves the handle to the full tier for good; the extra
+ * states then start from those reset values, so reset the affected envs (b747_reset / b747_reset_to_masked) after such
+ * an edit.  float64 handles integrate everything always. */
 
 /* Episode statistics accumulated in-kernel since the last call (then zeroed):
  * out[0]=episodes finished, out[1]=sum of episode returns, out[2]=sum of episode lengths (env steps),
