@@ -110,3 +110,30 @@ def test_argument_validation(libs):
     assert b"random reset" in L.b747_last_error()
     cfg = engine.make_cfg(n_envs=4, dtype=_lib.F32, env_layer=False)
     assert L.b747_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_ARG
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: every header under include/ compiles as C11 on its own (no torch, no C++)."""
+    import subprocess
+    for h in ("b747.h", "b747_scalar.h", "b747_scalar_legacy.h", "b747_params.h"):
+        src = tmp_path / f"use_{h}.c"
+        src.write_text(f'#include "{os.path.join(ROOT, "include", h)}"\nint main(void) {{ return 0; }}\n')
+        r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, (h, r.stderr)
+
+
+def test_shipped_library_is_sm100a_native():
+    """Static evidence in the shipped .so: sm_100a cubins only, TMA bulk copies (UBLKCP) + mbarrier (SYNCS) in the staged
+    step kernel, packed FP32 (FFMA2) in the model step, and -- by design, the path is not a contraction -- no tensor-core
+    opcodes (profiles/r2_sass_histogram.md is the full histogram)."""
+    import shutil
+    import subprocess
+    from b747_rl_ctrl_b200 import _lib
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
+    ops = set(re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\w+\s+)?([A-Z][A-Z0-9_]*)", sass, flags=re.M))
+    assert {"UBLKCP", "SYNCS", "FFMA2", "DFMA", "MUFU", "SHFL", "VOTE"} <= ops
+    assert not {o for o in ops if o.startswith(("HMMA", "UTCHMMA", "UTCQMMA", "HGMMA", "IMMA"))}
