@@ -421,11 +421,18 @@ def run_cuda(args, rank, local_rank, world):
             e1.close()
             return {"substeps": Kx, "kernel_ms": ms1, "env_steps_per_s": n_local / (ms1 * 1e-3), "achieved": ach1,
                     "peak": peak, "unit": "GB/s", "frac": ach1 / peak, "steps": n1, "episodes": ep1}
-        extra["k1"] = other_k(1)
-        extra["k5"] = other_k(5)
+        # secondary measurements never hide the headline: a failure is reported in place of the number
+        for key, Kx in (("k1", 1), ("k5", 5)):
+            try:
+                extra[key] = other_k(Kx)
+            except Exception as e:
+                extra[key] = {"error": repr(e)}
         # ---- the SB3-facing call: B747VecEnv.step (numpy mode) with float32 [N, 1] actions, terminal observations and
         # monitor records inside the timed region
-        extra_vec = _vecenv_rate(n_local, K, local_rank)
+        try:
+            extra_vec = _vecenv_rate(n_local, K, local_rank)
+        except Exception as e:
+            extra_vec = {"error": repr(e)}
     achieved = bytes_env * n_local / (kernel_ms * 1e-3) / 1e9
     prof = {}
     pj = os.path.join(ROOT, "profiles", "ncu_summary.json")
